@@ -1,0 +1,78 @@
+// plan.h -- host/device shared descriptors of the packed FlowChain weights and of the row sources.
+#pragma once
+#include <stdint.h>
+
+namespace fc {
+
+constexpr int kMaxBlocks = 8;    // coupling+BN pairs per CIF step (reference default 3, stress 6)
+constexpr int kMaxHidden = 4;    // hidden HxH layers per conditioner net (reference default 2)
+constexpr int kMaxSteps = 32;    // T
+
+// One dense layer of the fp32 path: W^T stored [K][NP] (NP = outputs padded to 8), bias [NP].
+struct LayerRef {
+    int32_t w;      // float offset into the packed fp32 buffer
+    int32_t b;
+    int32_t K;      // rows of W^T the kernel iterates (padded input width)
+    int32_t NP;     // padded outputs
+};
+
+// Packed description of one CIF step (reference CIF_step, fastpredNF.py:756-781).
+struct StepPlan {
+    int32_t C;        // conditioning width C_i = C0 + 2 i (dim of the auxiliary variable u)
+    int32_t c;        // C + 2 = input width of the r/q density nets
+    int32_t HP;       // density hidden width 2c padded to 8
+    int32_t CP;       // C padded to 8
+    int32_t HH;       // coupling hidden width H padded to 8
+    int32_t eps_off;  // column of this step in the separate noise tape
+    int32_t seq_eps_off;  // offset of block k in the sequential noise tape
+    int32_t n_blocks, n_hidden;
+    // density nets: [which: 0 = r_u_given_z, 1 = q_u_given_w][net: 0 = shift, 1 = log_scale][layer 0..2]
+    LayerRef dens[2][2][3];
+    // coupling nets: [block][net: 0 = s (tanh), 1 = t (relu)][layer 0 .. n_hidden]; the last Linear (H -> 2)
+    // is reduced to the single surviving output column (1 - mask) and stored as a vector.
+    LayerRef cpl[kMaxBlocks][2][kMaxHidden + 1];
+    int32_t cpl_last_w[kMaxBlocks][2];   // [HH] vector
+    float cpl_last_b[kMaxBlocks][2];
+    int32_t masked_dim[kMaxBlocks];      // index m with mask[m] == 1 (passes through); j = 1 - m is transformed
+    float bn_scale[kMaxBlocks][2], bn_shift[kMaxBlocks][2];      // forward:  y = scale * x + shift
+    float bn_iscale[kMaxBlocks][2], bn_ishift[kMaxBlocks][2];    // inverse:  x = iscale * y + ishift
+    float bn_ldj[kMaxBlocks];                                    // sum_d (log_gamma - 0.5 log(var + eps))
+    float std[2];                                                // clamp(var[step], 1e-4)
+    // ---- bf16 tensor-core path (byte offsets into the packed bf16 image) ----
+    int32_t tc_off;       // start of this step's image
+    int32_t tc_bytes;     // size (multiple of 16)
+};
+
+// A strided view: element (agent, point, step, d) at p[agent*sa + point*sp + step*st + d].
+struct Src {
+    const float* p;
+    long long sa, sp, st;
+};
+
+struct RowArgs {
+    Src x;         // query / trajectory points (.., 2)
+    Src prefix;    // conditioning-prefix trajectory (.., 2)
+    Src cond;      // encoder conditioning (.., C0)
+    Src base;      // base position (.., 2); st unused
+    const float* eps;      // noise tape or nullptr
+    long long eps_rs;      // row stride of eps
+    const float* z0;       // sampler: (N, 2) standard normals or nullptr
+    unsigned long long seed;
+    long long N;           // rows
+    long long PPA;         // rows per agent (G*K); agent = n / PPA, point = (n % PPA) / K
+    int K;
+    int prefix_is_query;   // 1: prefix/prev come from the row's own trajectory x (reference semantics)
+    float* out;            // element (agent, n % PPA, t) at out[agent*out_sa + (n%PPA)*out_sp + t*out_st]
+    long long out_sa, out_sp, out_st;
+    int seq_klo;           // sequential: lowest chain step applied (0, or T - n_step)
+    int seq_jlo;           // sequential: first result index written (0, or T - n_step - 1)
+};
+
+struct SampleOut {
+    float* seq;       // (N, T, 2)
+    float* log_prob;  // (N, T)
+    float* ldjs;      // (N, T)
+    float* base_lp;   // (N)
+};
+
+}  // namespace fc

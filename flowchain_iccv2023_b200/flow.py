@@ -1,0 +1,248 @@
+"""Host-side mirror of the reference flow interface for the density hot path.
+
+Class, method and state_dict names follow the reference (src/models/TP/fastpredNF.py:380-826,
+src/models/TP/TFCondARFlow.py:254-402) so a reference checkpoint loads unchanged and callers
+(`fastpredNF_TP`, src/main.py) need no edits.  The modules only OWN the parameters; all
+arithmetic of the path runs in the fused sm_100a kernels behind ``torch.ops.flowchain.*``.
+There is no PyTorch/CPU fallback -- without the CUDA library every density call raises.
+
+Noise: the reference draws ``torch.randn_like`` inside every CIF step (log_prob is stochastic,
+SURVEY §0 D7).  Here each call takes ``eps=`` (a noise tape, layouts in include/flowchain_b200.h)
+for parity runs, or ``seed=`` for the in-kernel Philox generator; with neither, a fresh seed is
+drawn from torch's default generator so repeated calls differ like the reference's.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+from torch.distributions import Normal
+
+from . import _lib, ops, packing
+from .synth import FlowSpec
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter holders (same registration order / keys as the reference modules)
+# ------------------------------------------------------------------------------------------------
+
+class _Fused(nn.Module):
+    def forward(self, *a, **k):
+        raise RuntimeError(
+            f"{type(self).__name__} only holds parameters: its arithmetic is fused into the flowchain CUDA "
+            "kernels -- call the flow's log_prob / log_prob_sequential / sample_with_log_prob instead")
+
+
+def _mlp(dims, act):
+    layers = []
+    for l in range(len(dims) - 1):
+        layers.append(nn.Linear(dims[l], dims[l + 1]))
+        if l < len(dims) - 2:
+            layers.append(act())
+    return nn.Sequential(*layers)
+
+
+class LinearMaskedCoupling(_Fused):
+    """Parameters of the masked affine coupling (TFCondARFlow.py:336-358): mask, s_net (Tanh), t_net (ReLU)."""
+
+    def __init__(self, input_size, hidden_size, n_hidden, mask, cond_label_size):
+        super().__init__()
+        self.register_buffer("mask", mask)
+        dims = [input_size + cond_label_size] + [hidden_size] * (n_hidden + 1) + [input_size]
+        self.s_net = _mlp(dims, nn.Tanh)
+        self.t_net = _mlp(dims, nn.ReLU)
+        self.t_net.load_state_dict(self.s_net.state_dict())   # the reference deep-copies s_net into t_net
+
+
+class BatchNorm(_Fused):
+    """Parameters of the invertible batch-norm layer (TFCondARFlow.py:275-284); eval statistics only."""
+
+    def __init__(self, input_size, momentum=0.9, eps=1e-5):
+        super().__init__()
+        self.momentum, self.eps = momentum, eps
+        self.log_gamma = nn.Parameter(torch.zeros(input_size))
+        self.beta = nn.Parameter(torch.zeros(input_size))
+        self.register_buffer("running_mean", torch.zeros(input_size))
+        self.register_buffer("running_var", torch.ones(input_size))
+
+
+class FlowSequential(nn.Sequential):
+    """Container [coupling, BN] x n_blocks (TFCondARFlow.py:254)."""
+
+    def forward(self, *a, **k):
+        return _Fused.forward(self)
+
+
+class DiagonalGaussianConditionalDensity(_Fused):
+    """Parameters of r(u|z,y) / q(u|w,y) (fastpredNF.py:690-699)."""
+
+    def __init__(self, cond_dim, out_dim):
+        super().__init__()
+        self.shift_net = _mlp([cond_dim, 2 * cond_dim, 2 * cond_dim, out_dim], nn.ReLU)
+        self.log_scale_net = _mlp([cond_dim, 2 * cond_dim, 2 * cond_dim, out_dim], nn.ReLU)
+
+
+class CIF_step(_Fused):
+    """One continuously-indexed flow step (fastpredNF.py:756-767)."""
+
+    def __init__(self, bijection, input_size, cond_label_size):
+        super().__init__()
+        self.bijection = bijection
+        self.cond_label_size = cond_label_size
+        self.r_u_given_z = DiagonalGaussianConditionalDensity(input_size + cond_label_size, cond_label_size)
+        self.q_u_given_w = DiagonalGaussianConditionalDensity(input_size + cond_label_size, cond_label_size)
+
+
+def create_RealNVP_step(n_blocks, input_size, hidden_size, n_hidden, cond_label_size):
+    """fastpredNF.py:610-628: alternating masks, BatchNorm after every coupling."""
+    modules = []
+    mask = torch.arange(input_size).float() % 2
+    for _ in range(n_blocks):
+        modules += [LinearMaskedCoupling(input_size, hidden_size, n_hidden, mask, cond_label_size)]
+        mask = 1 - mask
+        modules += [BatchNorm(input_size)]
+    return FlowSequential(*modules)
+
+
+# ------------------------------------------------------------------------------------------------
+# the flow
+# ------------------------------------------------------------------------------------------------
+
+class fastpredNF_CIF_separate_cond(nn.Module):
+    """Drop-in for the reference class of the same name (fastpredNF.py:814-826 + base classes :380-607)."""
+
+    def __init__(self, input_size: int, n_blocks: int, hidden_size: int, n_hidden: int, cond_label_size: int,
+                 **kwargs):
+        super().__init__()
+        arch = kwargs.get("flow_architecture", "realNVP")
+        if arch != "realNVP":
+            raise NotImplementedError(f"flow_architecture {arch!r}: only 'realNVP' is on the accelerated path "
+                                      "(no shipped config selects MAF, SURVEY §2)")
+        if input_size != 2:
+            raise NotImplementedError("the fused kernels require input_size == 2")
+        pred_len = kwargs["pred_len"]
+        self.input_size = input_size
+        self.spec = FlowSpec(pred_len=pred_len, input_size=input_size, cond_size=cond_label_size,
+                             hidden_size=hidden_size, n_hidden=n_hidden, n_blocks=n_blocks)
+        self.net = nn.ModuleList([
+            CIF_step(create_RealNVP_step(n_blocks, input_size, hidden_size, n_hidden, cond_label_size + i * input_size),
+                     input_size, cond_label_size + i * input_size)
+            for i in range(pred_len)])
+        self.var = nn.Parameter(torch.ones(pred_len, input_size) / 10, requires_grad=True)
+        self.precision = _lib.FC_PREC_FP32       # default arithmetic path of the MLPs
+        self.check_versions = True               # re-pack automatically when parameters change in place
+        self._handle: Optional[ops.Handle] = None
+        self._packed_version = None
+        self._tensors = None
+
+    # -- native handle management ---------------------------------------------------------------
+    def _param_version(self):
+        if self._tensors is None:
+            self._tensors = list(self.parameters()) + list(self.buffers())
+        v = 0
+        for t in self._tensors:
+            v += t._version
+        return v
+
+    def invalidate(self):
+        """Force a re-pack of the weights on the next call (after training `update()` / load)."""
+        self._packed_version = None
+        self._tensors = None
+
+    def _load_from_state_dict(self, *a, **k):
+        super()._load_from_state_dict(*a, **k)
+        self.invalidate()
+
+    def engine(self) -> ops.Handle:
+        dev = self.var.device
+        if dev.type != "cuda":
+            raise RuntimeError("flowchain_b200: move the flow to a CUDA device first (.cuda()); there is no CPU fallback")
+        if self._handle is None or self._handle.device != dev:
+            if self._handle is not None:
+                self._handle.close()
+            self._handle = ops.Handle(self.spec, dev)
+            self.invalidate()
+        if self._packed_version is None or (self.check_versions and self._packed_version != self._param_version()):
+            ver = self._param_version()
+            blob = packing.flatten_state(self.spec, self.state_dict())
+            self._handle.load_weights(blob, ver)
+            self._packed_version = ver
+        return self._handle
+
+    @staticmethod
+    def _seed(seed):
+        if seed is not None:
+            return int(seed) & 0x7FFFFFFFFFFFFFFF
+        return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+    def _dev(self, t, like=None):
+        if t is None:
+            return None
+        return t.to(device=self.var.device, dtype=torch.float32, non_blocking=True).contiguous()
+
+    # -- reference API ----------------------------------------------------------------------------
+    def base_dist(self, base_pos, step=0):
+        """fastpredNF.base_dist (fastpredNF.py:401-402)."""
+        return Normal(base_pos, torch.clamp(self.var[step], min=1e-4))
+
+    @torch.no_grad()
+    def log_prob(self, base_pos, x, cond, eps=None, seed=None, precision=None):
+        """flow.log_prob == log_prob_separate (fastpredNF.py:450-452, 460-465): (N,2),(N,T,2),(N,T,C0) -> (N,T)."""
+        h = self.engine()
+        src = x.device
+        out = torch.ops.flowchain.log_prob(
+            h.id, self._dev(base_pos), self._dev(x), self._dev(cond), self._dev(eps),
+            0 if eps is not None else self._seed(seed), self.precision if precision is None else precision)
+        return out.to(src)
+
+    log_prob_separate = log_prob
+
+    @torch.no_grad()
+    def log_prob_sequential(self, base_pos, x, cond, n_step=None, eps=None, seed=None, precision=None):
+        """fastpredNF.log_prob_sequential (fastpredNF.py:454-458): full chain, (N,T) or (N,n_step+1)."""
+        h = self.engine()
+        src = x.device
+        out = torch.ops.flowchain.log_prob_sequential(
+            h.id, self._dev(base_pos), self._dev(x), self._dev(cond), self._dev(eps),
+            0 if eps is not None else self._seed(seed), -1 if n_step is None else int(n_step),
+            self.precision if precision is None else precision)
+        return out.to(src)
+
+    @torch.no_grad()
+    def sample_with_log_prob(self, base_pos, cond, z0=None, eps=None, seed=None):
+        """fastpredNF.sample_with_log_prob (fastpredNF.py:472-477).
+
+        Accepts the reference's expanded arguments base_pos (B,S,2), cond (B,S,T,C0) (stride-0
+        expands are fine: only [:,0] is read -- the reference passes per-agent values expanded over
+        S, fastpredNF.py:106-108).  Returns (seq (B,S,T,2), log_prob (B,S,T), ldjs (B,S,T), base_lp (B,S,1))."""
+        h = self.engine()
+        src = base_pos.device
+        if base_pos.dim() != 3 or cond.dim() != 4:
+            raise RuntimeError("sample_with_log_prob expects base_pos (B,S,2) and cond (B,S,T,C0)")
+        B, S = base_pos.shape[0], base_pos.shape[1]
+        bp = self._dev(base_pos[:, 0])
+        cd = self._dev(cond[:, 0])
+        z0 = None if z0 is None else self._dev(z0).reshape(B * S, 2)
+        eps = None if eps is None else self._dev(eps).reshape(B * S, -1)
+        outs = torch.ops.flowchain.sample_with_log_prob(h.id, bp, cd, S, z0, eps, self._seed(seed), _lib.FC_PREC_FP32)
+        return tuple(o.to(src) for o in outs)
+
+    @torch.no_grad()
+    def grid_log_prob(self, base_pos, cond, grid, cond_traj=None, sequential=False, K=1, eps=None, seed=None,
+                      map_layout=False, precision=None):
+        """Working version of the reference's dead `predict_forward` (fastpredNF.py:166-184): log p for every
+        agent x grid point x step.  base_pos (A,2), cond (A,T,C0), grid (G,2) -> (A,G,T) (or (A,T,G) maps).
+        cond_traj=None: prefix mode "self" (x[:, i] = g, one literal reference call); cond_traj (A,T,2):
+        prefix mode "shared".  K > 1: importance-sampled CIF bound (extension; K = 1 is the reference)."""
+        h = self.engine()
+        src = grid.device
+        out = torch.ops.flowchain.grid_log_prob(
+            h.id, self._dev(base_pos), self._dev(cond), self._dev(cond_traj), self._dev(grid), self._dev(eps),
+            0 if eps is not None else self._seed(seed),
+            _lib.FC_PREFIX_SELF if cond_traj is None else _lib.FC_PREFIX_SHARED, bool(sequential), int(K),
+            bool(map_layout), self.precision if precision is None else precision)
+        return out.to(src)
+
+    def forward(self, *a, **k):
+        return _Fused.forward(self)

@@ -1,0 +1,146 @@
+"""Host-side mirror of the reference model wrapper ``fastpredNF_TP`` for the density hot path
+(reference: src/models/TP/fastpredNF.py:21-243; model protocol src/models/build_model.py:22-39).
+
+Kept: ``predict(data_dict, return_prob)``, ``predict_from_new_obs(data_dict, time_step)``,
+``get_base_pos``, ``save / load / check_saved_path``, the ``data_dict`` keys
+(``("prob_st", k)`` (B,S,T-k,3), ``("pred_st", k)`` (B,T-k,2)) and the module-level update cache
+(``ldjs_tmp``, ``base_prob_normalizer_tmp``).  Added: a working ``predict_forward`` (dense grid).
+The history encoder is NOT part of this path (north_star (d)): pass any callable
+``encoder(data_dict) -> (B, T, C0)`` (a PyTorch module in production, a stub in tests/bench).
+``update()`` (the Adam training step) is out of scope for this tier and raises.
+"""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import Callable, Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from .flow import fastpredNF_CIF_separate_cond
+
+
+class fastpredNF_TP(nn.Module):
+    def __init__(self, cfg=None, encoder: Optional[Callable] = None, pred_len: int = 12, obs_len: int = 8,
+                 pred_state: str = "state_v", n_blocks: int = 3, n_hidden: int = 2, hidden_size: int = 64,
+                 cond_size: int = 16, output_path: Optional[str] = None):
+        super().__init__()
+        if cfg is not None:   # duck-typed yacs node (src/default_params.py)
+            pred_len = cfg.DATA.PREDICT_LENGTH
+            obs_len = cfg.DATA.OBSERVE_LENGTH
+            pred_state = cfg.DATA.TP.PRED_STATE
+            n_blocks = cfg.MODEL.FLOW.N_BLOCKS
+            n_hidden = cfg.MODEL.FLOW.N_HIDDEN
+            hidden_size = cfg.MODEL.FLOW.HIDDEN_SIZE
+            cond_size = cfg.MODEL.FLOW.CONDITIONING_LENGTH
+            output_path = cfg.OUTPUT_DIR
+        self.output_path = Path(output_path) if output_path is not None else Path("output")
+        self.obs_len, self.pred_len, self.pred_state = obs_len, pred_len, pred_state
+        self.output_size = 2
+        self.encoder = encoder
+        self.flow = fastpredNF_CIF_separate_cond(input_size=2, n_blocks=n_blocks, n_hidden=n_hidden,
+                                                 hidden_size=hidden_size, cond_label_size=cond_size,
+                                                 flow_architecture="realNVP", pred_len=pred_len)
+        self.optimizers = []
+        self.sample_num_prob = 10000     # fastpredNF.py:104
+        self.sample_num_ml = 100         # fastpredNF.py:126
+        self.ldjs_tmp = None
+        self.base_prob_normalizer_tmp = None
+
+    # ---- model protocol -------------------------------------------------------------------------
+    def predict(self, data_dict: Dict, return_prob: bool = True, **noise) -> Dict:
+        if return_prob:
+            return self.predict_inverse_prob(data_dict, **noise)
+        return self.predict_inverse_ML(data_dict, **noise)
+
+    def _sample(self, data_dict, sample_num, **noise):
+        dist_args = self.encoder(data_dict)                                       # (B, T, C0)
+        base_pos = self.get_base_pos(data_dict)[:, None].expand(-1, sample_num, -1)
+        dist_args = dist_args[:, None].expand(-1, sample_num, -1, -1)
+        return self.flow.sample_with_log_prob(base_pos, cond=dist_args, **noise)
+
+    @torch.no_grad()
+    def predict_inverse_prob(self, data_dict: Dict, **noise) -> Dict:
+        """fastpredNF.py:101-121."""
+        sampled_seq, log_prob, seq_ldjs, base_log_prob = self._sample(data_dict, self.sample_num_prob, **noise)
+        self.ldjs_tmp = seq_ldjs                                                  # cache for the rapid update
+        h = self.flow.engine()
+        self.base_prob_normalizer_tmp = torch.ops.flowchain.base_normalizer(
+            h.id, base_log_prob.to(self.flow.var.device).contiguous()).to(base_log_prob.device)
+        data_dict[("prob_st", 0)] = torch.cat([sampled_seq, log_prob[..., None]], dim=-1)
+        data_dict[("pred_st", 0)] = sampled_seq[:, -1]
+        return data_dict
+
+    @torch.no_grad()
+    def predict_inverse_ML(self, data_dict: Dict, **noise) -> Dict:
+        """fastpredNF.py:123-140."""
+        sampled_seq, _, _, _ = self._sample(data_dict, self.sample_num_ml, **noise)
+        pred = sampled_seq[:, -1]
+        if torch.sum(torch.isnan(pred)):
+            pred = torch.where(torch.isnan(pred), data_dict["obs_st"][:, 0, None, 2:4].expand(pred.size()), pred)
+        data_dict[("pred_st", 0)] = pred
+        return data_dict
+
+    @torch.no_grad()
+    def predict_from_new_obs(self, data_dict: Dict, time_step: int) -> Dict:
+        """Rapid update (fastpredNF.py:142-164); batched = vmap of the B = 1 reference call over agents."""
+        assert 0 < time_step and time_step < self.pred_len, \
+            f"time_step for update need to be 0~{self.pred_len-1}, got {time_step}"
+        assert ("prob_st", 0) in data_dict.keys(), "Initial prediction needed before updating"
+        h = self.flow.engine()
+        dev = self.flow.var.device
+        prob0 = data_dict[("prob_st", 0)]
+        src = prob0.device
+        out = torch.ops.flowchain.update(
+            h.id, data_dict["gt_st"][:, time_step - 1].to(dev, torch.float32).contiguous(), time_step,
+            prob0.to(dev).contiguous(), self.ldjs_tmp.to(dev).contiguous(),
+            self.base_prob_normalizer_tmp.to(dev).contiguous())
+        data_dict[("prob_st", time_step)] = out.to(src)
+        data_dict[("pred_st", time_step)] = data_dict[("pred_st", 0)][:, time_step:]
+        return data_dict
+
+    @torch.no_grad()
+    def predict_forward(self, data_dict: Dict, sample_num_per_dim: int = 200, lo: float = -3.0, hi: float = 3.0,
+                        cond_traj=None, sequential: bool = False, **kw) -> Dict:
+        """Working version of the reference's dead grid evaluation (fastpredNF.py:166-184):
+        ("prob_st", 0) = cat[grid, log_prob] of shape (B, G, T, 3) on the lattice linspace(lo,hi,n)^2."""
+        dist_args = self.encoder(data_dict)
+        base_pos = self.get_base_pos(data_dict)
+        dev = self.flow.var.device
+        ax = torch.linspace(lo, hi, steps=sample_num_per_dim, device=dev)
+        grid = torch.cartesian_prod(ax, ax)
+        lp = self.flow.grid_log_prob(base_pos, dist_args, grid, cond_traj=cond_traj, sequential=sequential, **kw)
+        B, G, T = lp.shape
+        seq = grid[None, :, None, :].expand(B, G, T, 2)
+        data_dict[("prob_st", 0)] = torch.cat([seq, lp[..., None]], dim=-1)
+        return data_dict
+
+    def update(self, data_dict: Dict) -> Dict:
+        raise NotImplementedError(
+            "fastpredNF_TP.update is the Adam training step (fastpredNF.py:186-202); training stays on the "
+            "reference PyTorch modules and is out of scope of the B200 density path (SURVEY §3.4)")
+
+    def get_base_pos(self, data_dict: Dict) -> torch.Tensor:
+        """fastpredNF.py:204-213."""
+        if self.pred_state == "state_p":
+            return data_dict["obs_st"][:, -1, :2]
+        elif self.pred_state == "state_v":
+            return data_dict["obs_st"][:, -1, 2:4]
+        elif self.pred_state == "state_a":
+            return data_dict["obs_st"][:, -1, 4:6]
+        raise ValueError
+
+    def save(self, epoch: int = 0, path: Path = None) -> None:
+        path = self.output_path / "ckpt.pt" if path is None else path
+        torch.save({"epoch": epoch, "state": self.state_dict(), "optim_state": {}}, path)
+
+    def check_saved_path(self, path: Path = None) -> bool:
+        path = self.output_path / "ckpt.pt" if path is None else path
+        return Path(path).exists()
+
+    def load(self, path: Path = None) -> int:
+        path = self.output_path / "ckpt.pt" if path is None else path
+        ckpt = torch.load(path, map_location="cpu")
+        self.load_state_dict(ckpt["state"], strict=False)
+        self.flow.invalidate()
+        return ckpt["epoch"]

@@ -1,0 +1,114 @@
+/* flowchain_b200.h -- C-ABI of the B200-native FlowChain analytical-density hot path.
+ *
+ * The reference (meaten/FlowChain-ICCV2023) is pure Python/PyTorch and has NO FFI/plugin layer;
+ * its boundary for this path is the flow object's methods and three methods of the model wrapper
+ * (SURVEY.md §8b).  Each entry point below names the reference method it replaces; a maintainer
+ * binds it with the ctypes stub shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - every data pointer is a DEVICE pointer to contiguous float32 unless stated otherwise; the
+ *    caller owns all buffers; calls enqueue on `stream` (a cudaStream_t passed as void*), never
+ *    synchronise, and are CUDA-graph capturable;
+ *  - return value 0 = ok, non-zero = error; message via fc_last_error(); no C++ exceptions cross;
+ *  - a handle is thread-compatible (one caller at a time); distinct handles are independent;
+ *  - noise: `eps` (and `z0`) inject the CIF auxiliary draws (noise tape, layouts below); when
+ *    NULL the kernels draw their own Philox4x32-10 normals from `seed` (production mode);
+ *  - D (input_size) must be 2 and the coupling masks one-hot, as in every shipped config.
+ *
+ * Noise-tape layouts (rows N):
+ *    separate / sampler : eps (N, E), E = sum_i C_i, step i at columns [off_i, off_i + C_i), C_i = C0 + 2 i
+ *    sequential         : eps (N, sum_k (T-k) C_k); block k = the (N, T-k, C_k) draw of chain step k,
+ *                         result index j at position j-k inside the block
+ */
+#ifndef FLOWCHAIN_B200_H
+#define FLOWCHAIN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fc_handle fc_handle;
+
+/* MODEL.FLOW.* knobs (reference: src/default_params.py:30-35; ctor fastpredNF.py:58-70, 815-826). */
+typedef struct fc_model_desc {
+    int32_t pred_len;     /* T  : chained CIF steps (DATA.PREDICT_LENGTH)        */
+    int32_t input_size;   /* D  : flow dimension, must be 2                      */
+    int32_t cond_size;    /* C0 : MODEL.FLOW.CONDITIONING_LENGTH                 */
+    int32_t hidden_size;  /* H  : MODEL.FLOW.HIDDEN_SIZE                         */
+    int32_t n_hidden;     /*      MODEL.FLOW.N_HIDDEN                            */
+    int32_t n_blocks;     /*      MODEL.FLOW.N_BLOCKS (coupling+BN pairs / step) */
+} fc_model_desc;
+
+/* arithmetic path of the conditioner / auxiliary-density MLPs */
+enum { FC_PREC_FP32 = 0,   /* CUDA-core fp32, parity 1e-4 (+rel) nats                         */
+       FC_PREC_BF16 = 1 }; /* tcgen05 tensor cores, bf16 operands / fp32 accumulate, 5e-3 (+rel) */
+
+/* prefix modes of the dense-grid evaluation */
+enum { FC_PREFIX_SELF = 0,     /* x[:, i] = g for every step (the literal reference call)   */
+       FC_PREFIX_SHARED = 1 }; /* prefix = per-agent conditioning trajectory cond_traj      */
+
+/* Replaces: fastpredNF_TP.__init__ building self.flow (fastpredNF.py:58-70).  device = CUDA ordinal. */
+int fc_create(fc_handle** out, const fc_model_desc* desc, int device);
+void fc_destroy(fc_handle* h);
+/* Last error text of `h` (or of the failed fc_create when h == NULL). */
+const char* fc_last_error(const fc_handle* h);
+
+/* Number of floats of the canonical weight blob for `desc` (layout: flowchain_iccv2023_b200/packing.py). */
+size_t fc_weight_blob_floats(const fc_model_desc* desc);
+/* Replaces: reading flow.state_dict() (fastpredNF.py:233-243 load path).  `host_blob` is a HOST pointer to
+ * the canonical fp32 blob; it is re-laid-out for the kernels and uploaded.  `version` is remembered so the
+ * host can re-pack after a training update().  Synchronises `stream` (one-off). */
+int fc_load_weights(fc_handle* h, const float* host_blob, size_t n_floats, uint64_t version, void* stream);
+uint64_t fc_weights_version(const fc_handle* h);
+
+/* Replaces: fastpredNF.log_prob -> log_prob_separate -> forward_separate (fastpredNF.py:450-465, 571-584).
+ * base_pos (N,2), x (N,T,2), cond (N,T,C0), eps (N,E)|NULL -> out (N,T). */
+int fc_log_prob(fc_handle* h, const float* base_pos, const float* x, const float* cond,
+                const float* eps, uint64_t seed, float* out, int64_t N, int precision, void* stream);
+
+/* Replaces: fastpredNF.log_prob_sequential -> forward_sequential(seq, cond, n_step) (fastpredNF.py:454-458,
+ * 548-569).  n_step < 0 means None.  out (N, n_out), n_out = T (None) or n_step+1. */
+int fc_log_prob_sequential(fc_handle* h, const float* base_pos, const float* x, const float* cond,
+                           const float* eps, uint64_t seed, int n_step, float* out, int64_t N,
+                           int precision, void* stream);
+
+/* Working version of the reference's dead predict_forward (fastpredNF.py:166-184):
+ * log p for every agent x grid point x step without materialising the expanded rows.
+ * base_pos (A,2), cond (A,T,C0), cond_traj (A,T,2) (FC_PREFIX_SHARED only, else NULL), grid (G,2),
+ * eps (A*G*K, E or sequential width)|NULL.  sequential != 0 evaluates the full chain (a9) instead of
+ * the per-step density (a8).  K >= 1 importance samples of the CIF auxiliary variable (K = 1 is the
+ * reference; K > 1 returns logsumexp_k - log K, rows ordered (a, g, k)).
+ * out: element (a, g, t) at out[a*out_agent_stride + g*out_point_stride + t*out_step_stride]. */
+int fc_grid_log_prob(fc_handle* h, const float* base_pos, const float* cond, const float* cond_traj,
+                     const float* grid, const float* eps, uint64_t seed, int prefix_mode, int sequential,
+                     int K, float* out, int64_t out_agent_stride, int64_t out_point_stride,
+                     int64_t out_step_stride, int64_t A, int64_t G, int precision, void* stream);
+
+/* Replaces: fastpredNF.sample_with_log_prob -> fastpredNF_separate_cond.inverse (fastpredNF.py:472-477,
+ * 586-607).  base_pos (B,2), cond (B,T,C0) are per agent and expanded over the S samples on the fly
+ * (the reference expands them, fastpredNF.py:106-108).  z0 (B*S,2)|NULL is the standard-normal base
+ * draw (u0 = base_pos + std0*z0), eps (B*S,E)|NULL.
+ * Outputs: seq (B,S,T,2), log_prob (B,S,T), ldjs (B,S,T), base_lp (B,S). */
+int fc_sample_with_log_prob(fc_handle* h, const float* base_pos, const float* cond, const float* z0,
+                            const float* eps, uint64_t seed, float* seq, float* log_prob, float* ldjs,
+                            float* base_lp, int64_t B, int64_t S, int precision, void* stream);
+
+/* normalizer[a] = sum_s exp(base_lp[a,s])  (fastpredNF.py:114 base_prob_normalizer_tmp). */
+int fc_base_normalizer(fc_handle* h, const float* base_lp, float* normalizer, int64_t A, int64_t S, void* stream);
+
+/* Replaces: fastpredNF_TP.predict_from_new_obs (fastpredNF.py:142-164), vmapped over agents (the reference
+ * only works at B = 1).  new_pos (A,2) = gt_st[:, t-1]; prob_st_0 (A,S,T,3); ldjs (A,S,T); normalizer (A)
+ * -> prob_st_t (A,S,T-t,3).  0 < time_step < T. */
+int fc_update(fc_handle* h, const float* new_pos, int time_step, const float* prob_st_0, const float* ldjs,
+              const float* normalizer, float* prob_st_t, int64_t A, int64_t S, void* stream);
+
+/* Number of kernels this library has launched on behalf of `h` since creation (bench.py's gpu_launches). */
+uint64_t fc_launch_count(const fc_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOWCHAIN_B200_H */
