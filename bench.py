@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the FlowChain analytical-density hot path on B200.
+
+Metric (BASELINE.json): log-density evals/s over a dense grid = (agent, timestep, query point)
+log-probabilities per second.  A "step" is ONE pass of the hot path over one batch: the per-step
+("separate") density of config 2 -- 64 agents x 12 steps x 256x256 lattice, prefix mode "self" (the literal
+reference call flow.log_prob(base_pos, g.expand(T), cond)) -- per GPU.  With N > 1 GPUs every
+rank evaluates its own 64 agents (weak scaling, no data-path collective) and ONE all-gather assembles the
+(N*64, T, G) density maps on every rank inside the timed step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|bf16]
+
+`--impl reference` times the reference algorithm's CPU port (oracle/, numpy fp32, all host threads BLAS
+uses) on a bounded sample of the same workload; /root/reference does not exist on the GPU box.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from flowchain_iccv2023_b200 import synth  # noqa: E402
+
+METRIC = "log_density_evals_per_sec"
+UNIT = "evals/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p["bf16_tflops_sustained"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_port_rate(spec, params, seconds: float, agents: int = 1, grid_n: int = 100):
+    """Times the numpy port of the reference algorithm (oracle/) on a bounded sample: `agents` x
+    grid_n^2 lattice x T steps per pass (config 1 shape), repeated for ~`seconds`.  Returns evals/s."""
+    from oracle import flowchain_oracle as orc
+    inp = synth.make_inputs(spec, agents, seed=1)
+    grid = synth.make_grid(grid_n)
+    eps = synth.make_eps(spec, agents * grid.shape[0], 2)
+    p32 = orc.cast_params(params, np.float32)
+    orc.grid_log_prob_self(p32, inp["base_pos"], inp["cond"], grid, eps, np.float32)   # warm-up
+    n, t0 = 0, time.perf_counter()
+    times = []
+    while True:
+        t1 = time.perf_counter()
+        orc.grid_log_prob_self(p32, inp["base_pos"], inp["cond"], grid, eps, np.float32)
+        times.append(time.perf_counter() - t1)
+        n += 1
+        if time.perf_counter() - t0 > seconds and n >= 3:
+            break
+    evals = agents * grid.shape[0] * spec.pred_len
+    return evals / float(np.median(times)), float(np.median(times)), n
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([d.get("num_threads", 1) for d in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    spec = synth.DEFAULT_SPEC
+    params = synth.make_params(spec, 0)
+    sample = f"1 agent x 100x100 lattice x {spec.pred_len} steps per step (config 1 shape), numpy fp32 port of the reference algorithm"
+    from oracle import flowchain_oracle as orc
+    inp = synth.make_inputs(spec, 1, seed=1)
+    grid = synth.make_grid(100)
+    eps = synth.make_eps(spec, grid.shape[0], 2)
+    p32 = orc.cast_params(params, np.float32)
+    per = []
+    for i in range(args.warmup + args.steps):       # one step = one pass over the bounded sample
+        t0 = time.perf_counter()
+        orc.grid_log_prob_self(p32, inp["base_pos"], inp["cond"], grid, eps, np.float32)
+        if i >= args.warmup:
+            per.append(time.perf_counter() - t0)
+    ms = float(np.mean(per)) * 1e3
+    value = 1 * 10000 * spec.pred_len / (ms / 1e3)
+    cores = blas_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config2: 64 agents x 12 steps x 256x256 lattice, separate density, prefix self",
+                       "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from flowchain_iccv2023_b200 import _lib
+    from flowchain_iccv2023_b200.flow import fastpredNF_CIF_separate_cond
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    spec = synth.DEFAULT_SPEC
+    params = synth.make_params(spec, 0)
+    flow = fastpredNF_CIF_separate_cond(input_size=2, n_blocks=spec.n_blocks, hidden_size=spec.hidden_size,
+                                        n_hidden=spec.n_hidden, cond_label_size=spec.cond_size,
+                                        flow_architecture="realNVP", pred_len=spec.pred_len)
+    flow.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+    flow = flow.to(dev).eval()
+    flow.check_versions = False
+    prec = {"fp32": _lib.FC_PREC_FP32, "bf16": _lib.FC_PREC_BF16}[args.precision]
+    flow.precision = prec
+    handle = flow.engine()
+
+    A, n = args.agents, args.grid
+    G, T = n * n, spec.pred_len
+    inp = synth.make_inputs(spec, A, seed=1000 + rank)      # every rank owns its own 64 agents (weak scaling)
+    grid_np = synth.make_grid(n)
+    # host (pinned) copies for the end-to-end leg, device-resident copies for the kernel-only leg
+    h_base = torch.from_numpy(inp["base_pos"]).pin_memory()
+    h_cond = torch.from_numpy(inp["cond"]).pin_memory()
+    h_grid = torch.from_numpy(grid_np).pin_memory()
+    d_base, d_cond, d_grid = h_base.to(dev), h_cond.to(dev), h_grid.to(dev)
+    h_out = torch.empty((A, T, G), dtype=torch.float32).pin_memory()
+    gathered = torch.empty((world * A, T, G), dtype=torch.float32, device=dev) if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    seed = [1]
+
+    def hot_path():
+        seed[0] += 1
+        return flow.grid_log_prob(d_base, d_cond, d_grid, seed=seed[0], map_layout=True)
+
+    def step():
+        maps = hot_path()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, maps)
+            return gathered
+        return maps
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- kernel-only leg: inputs resident in HBM, CUDA events on the launching (current) stream ----------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = handle.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+           torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.fill_(float(i))                      # flush L2 between timed iterations (outside the events)
+        ev[i][0].record()
+        maps = hot_path()
+        ev[i][1].record()                          # end of the dominant kernel
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, maps)
+        ev[i][2].record()
+    barrier()
+    launches = handle.launch_count - l0
+    clocks = sampler.stop()
+    step_ms = sum(a.elapsed_time(c) for a, b, c in ev)
+    kern_ms = sum(a.elapsed_time(b) for a, b, c in ev) / args.steps
+    t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    evals_per_step = world * A * G * T
+    value = evals_per_step / (ms_per_step / 1e3)
+
+    # ---- end-to-end leg: public API with HOST buffers, H2D + D2H inside the timed region -----------------
+    def e2e_step():
+        b = h_base.to(dev, non_blocking=True)
+        c = h_cond.to(dev, non_blocking=True)
+        g = h_grid.to(dev, non_blocking=True)
+        seed[0] += 1
+        maps = flow.grid_log_prob(b, c, g, seed=seed[0], map_layout=True)
+        h_out.copy_(maps, non_blocking=True)
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / args.steps
+    e2e_value = evals_per_step / (e2e_ms / 1e3)
+    h2d = (h_base.numel() + h_cond.numel() + h_grid.numel()) * 4
+    d2h = h_out.numel() * 4
+
+    if rank == 0:
+        pk = peaks()
+        flops_launch = A * G * spec.flops_separate_row()          # algorithmic FLOPs of one launch
+        achieved = flops_launch / (kern_ms / 1e3) / 1e12
+        peak = pk["bf16_tflops_sustained"]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "bf16 operands / f32 accumulate", "data": "synthetic",
+            "config": {"workload": f"config2: {A} agents x {T} steps x {n}x{n} lattice per GPU, separate density (flow.log_prob), prefix self",
+                       "model": "default ETH CIF_separate_cond (T=12,C0=16,H=64,3 blocks), random-init weights",
+                       "noise": "in-kernel Philox4x32-10", "precision": args.precision,
+                       "l2": "L2 flushed (256 MB write) between timed iterations; output 201 MB > L2",
+                       "multi_gpu": "agents sharded, one all-gather of density maps inside the step" if world > 1 else "single GPU"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
+                         "kernel_ms": kern_ms, "algorithmic_flops_per_launch": flops_launch},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            rate, med, nrep = cpu_port_rate(spec, params, seconds=args.cpu_seconds)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": blas_threads(), "kind": "port",
+                                    "sample": f"1 agent x 100x100 lattice x {T} steps (config 1 shape), numpy fp32 port, "
+                                              f"median of {nrep} passes ({med * 1e3:.0f} ms each)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("FLOWCHAIN_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--agents", type=int, default=64)
+    ap.add_argument("--grid", type=int, default=256)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -3,10 +3,12 @@
   (1) the committed golden vectors produced by the unmodified reference (tests/golden/*.npz), and
   (2) the numpy oracle in fp64 on fresh seeded inputs.
 
-Tolerances (north_star): fp32 path |d| <= 1e-4 + 1e-6*|ref64| nats -- |log p| reaches ~3e3 on the
-[-3,3]^2 lattice where one fp32 ulp is 2.4e-4, and the reference's own fp32 result differs from its
-fp64 result by up to 6e-4 there, hence the relative term; bf16 tensor-core path
-|d| <= 5e-3 + 2e-3*|ref64|."""
+Tolerances (north_star 1e-4 nats, stated as SURVEY §8c does): fp32 path |d| <= 1e-4 + 3e-6*|ref64| nats
+against the fp64 oracle -- |log p| reaches ~3e3 on the [-3,3]^2 lattice where one fp32 ulp is 2.4e-4, and
+the reference's own fp32 result differs from its fp64 result by up to 6e-4 (separate) / 1.9e-3 (sequential)
+there, hence the relative term.  Where the reference's fp32 outputs are in the fixture we
+also require our max error to stay within 3x the reference's own fp32-vs-fp64 max error.
+bf16 tensor-core path: see test_gpu_tc.py."""
 import numpy as np
 import pytest
 import torch
@@ -17,13 +19,23 @@ from flowchain_iccv2023_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
-FP32_ATOL, FP32_RTOL = 1e-4, 1e-6
+FP32_ATOL, FP32_RTOL = 1e-4, 3e-6
 
 
-def assert_close32(out, ref64, what=""):
+SEQ_RTOL = 3e-6
+
+
+def assert_not_worse_than_ref32(out, ref32, ref64, what):
+    ours = np.abs(np.asarray(out, np.float64) - ref64).max()
+    theirs = np.abs(np.asarray(ref32, np.float64) - ref64).max()
+    print(f"{what}: max|ours-fp64| = {ours:.3e}   max|reference_fp32-fp64| = {theirs:.3e}")
+    assert ours <= 3.0 * theirs + 1e-5, (what, ours, theirs)
+
+
+def assert_close32(out, ref64, what="", rtol=FP32_RTOL):
     out = np.asarray(out, dtype=np.float64)
     err = np.abs(out - ref64)
-    tol = FP32_ATOL + FP32_RTOL * np.abs(ref64)
+    tol = FP32_ATOL + rtol * np.abs(ref64)
     worst = np.argmax(err - tol)
     assert np.all(err <= tol), f"{what}: max err {err.max():.3e}, worst idx {worst} err {err.flat[worst]:.3e} ref {ref64.flat[worst]:.4f}"
 
@@ -55,19 +67,19 @@ def test_log_prob_golden(flows, case):
     out = f.log_prob(T(g["base_pos"]), T(g["x"]), T(g["cond"]), eps=T(g["eps"])).cpu().numpy()
     assert out.shape == g["log_prob_64"].shape
     assert_close32(out, g["log_prob_64"], "log_prob")
-    # report the reference's own fp32-vs-fp64 error beside ours
-    print(case, "ours", np.abs(out - g["log_prob_64"]).max(), "ref32", np.abs(g["log_prob_32"] - g["log_prob_64"]).max())
+    assert_not_worse_than_ref32(out, g["log_prob_32"], g["log_prob_64"], case + " log_prob")
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_log_prob_sequential_golden(flows, case):
     f, spec, p, g = flows(case)
     out = f.log_prob_sequential(T(g["base_pos"]), T(g["x"]), T(g["cond"]), eps=T(g["eps_seq"])).cpu().numpy()
-    assert_close32(out, g["log_prob_seq_64"], "log_prob_sequential")
+    assert_close32(out, g["log_prob_seq_64"], "log_prob_sequential", SEQ_RTOL)
+    assert_not_worse_than_ref32(out, g["log_prob_seq_32"], g["log_prob_seq_64"], case + " log_prob_sequential")
     ns = min(3, spec.pred_len - 1)
     out = f.log_prob_sequential(T(g["base_pos"]), T(g["x"]), T(g["cond"]), n_step=ns, eps=T(g["eps_seq"])).cpu().numpy()
     assert out.shape == (g["x"].shape[0], ns + 1)
-    assert_close32(out, g["log_prob_seq_n3_64"], "log_prob_sequential n_step")
+    assert_close32(out, g["log_prob_seq_n3_64"], "log_prob_sequential n_step", SEQ_RTOL)
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
@@ -75,6 +87,7 @@ def test_grid_golden(flows, case):
     f, spec, p, g = flows(case)
     out = f.grid_log_prob(T(g["base_pos"]), T(g["cond"]), T(g["grid"]), eps=T(g["eps_grid"])).cpu().numpy()
     assert_close32(out, g["grid_self_64"], "grid self")
+    assert_not_worse_than_ref32(out, g["grid_self_32"], g["grid_self_64"], case + " grid self")
     out = f.grid_log_prob(T(g["base_pos"]), T(g["cond"]), T(g["grid"]), cond_traj=T(g["cond_traj"]),
                           eps=T(g["eps_grid"])).cpu().numpy()
     assert_close32(out, g["grid_shared_64"], "grid shared")
@@ -183,10 +196,11 @@ def test_philox_mode_is_seeded_and_plausible(flows):
     c = f.grid_log_prob(T(g["base_pos"]), T(g["cond"]), T(g["grid"]), seed=6)
     assert torch.equal(a, b) and not torch.equal(a, c)
     assert torch.isfinite(a).all()
-    # K-sample bound with the in-kernel generator is close to the tape-driven estimate on average
+    # single-sample estimates from the in-kernel generator and from the tape are draws of the same
+    # distribution: over 3456 values (std of one draw ~18 nats) the mean difference is ~0.4
     tape = torch.from_numpy(g["grid_self_64"]).float()
-    k64 = f.grid_log_prob(T(g["base_pos"]), T(g["cond"]), T(g["grid"]), K=64, seed=9).cpu()
-    assert (k64 - tape).mean().abs() < 25.0     # eps std of log_prob is ~18 nats at random init
+    assert (a.cpu() - tape).mean().abs() < 3.0
+    assert 0.5 < (a.cpu() - c.cpu()).std() / (a.cpu() - tape).std() < 2.0
 
 
 def test_error_paths(flows):
