@@ -453,3 +453,10 @@ extern "C" int fc_update(fc_handle* h, const float* new_pos, int t, const float*
     FC_CUDA(h, cudaGetLastError());
     return 0;
 }
+
+extern "C" int fc_tc_gemm_selftest(const float* A, const float* B, float* D, int N, int K, int device) {
+    std::string msg;
+    int rc = fc::tc_selftest(A, B, D, N, K, device, &msg);
+    if (rc) g_err = msg;
+    return rc;
+}

@@ -105,6 +105,11 @@ int fc_base_normalizer(fc_handle* h, const float* base_lp, float* normalizer, in
 int fc_update(fc_handle* h, const float* new_pos, int time_step, const float* prob_st_0, const float* ldjs,
               const float* normalizer, float* prob_st_t, int64_t A, int64_t S, void* stream);
 
+/* Diagnostic: D[128 x N] = A[128 x K] * B[N x K]^T on the tcgen05 tensor cores (bf16 operands, fp32
+ * accumulate) through the same descriptor / TMEM / mbarrier helpers the fused kernel uses.  HOST pointers,
+ * row-major fp32; N multiple of 16 in [16,256], K in [1,256].  Error text via fc_last_error(NULL). */
+int fc_tc_gemm_selftest(const float* A, const float* B, float* D, int N, int K, int device);
+
 /* Number of kernels this library has launched on behalf of `h` since creation (bench.py's gpu_launches). */
 uint64_t fc_launch_count(const fc_handle* h);
 
