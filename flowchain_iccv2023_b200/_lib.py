@@ -69,7 +69,7 @@ def load():
     lib.fc_base_normalizer.restype = c_int
     lib.fc_update.argtypes = [c_void_p, fp, c_int, fp, fp, fp, fp, c_int64, c_int64, c_void_p]
     lib.fc_update.restype = c_int
-    lib.fc_tc_gemm_selftest.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int]
+    lib.fc_tc_gemm_selftest.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int]
     lib.fc_tc_gemm_selftest.restype = c_int
     lib.fc_launch_count.argtypes = [c_void_p]
     lib.fc_launch_count.restype = c_uint64

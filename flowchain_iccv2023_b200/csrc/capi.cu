@@ -29,6 +29,8 @@ struct fc_handle {
     size_t wbuf_floats = 0;
     unsigned char* d_tc = nullptr;    // packed bf16 tensor-core image
     size_t tc_bytes = 0;
+    fc::TcStep* d_tcsteps = nullptr;
+    fc::TcDims tcdims{};
     float* d_scratch = nullptr;       // K>1 importance-sample staging
     size_t scratch_floats = 0;
     Dims dims{};
@@ -108,6 +110,7 @@ extern "C" void fc_destroy(fc_handle* h) {
     cudaFree(h->d_plans);
     cudaFree(h->d_wbuf);
     cudaFree(h->d_tc);
+    cudaFree(h->d_tcsteps);
     cudaFree(h->d_scratch);
     delete h;
 }
@@ -240,11 +243,13 @@ extern "C" int fc_load_weights(fc_handle* h, const float* blob, size_t n_floats,
 
     // bf16 tensor-core image (only for shapes that path supports; otherwise tc_bytes stays 0)
     std::vector<unsigned char> tc_img;
-    fc::tc_pack(d, plans, tcsrc, tc_img);
+    std::vector<fc::TcStep> tc_steps;
+    fc::tc_pack(d, plans, tcsrc, tc_img, tc_steps, h->tcdims);
 
     FC_CUDA(h, cudaFree(h->d_plans)); h->d_plans = nullptr;
     FC_CUDA(h, cudaFree(h->d_wbuf)); h->d_wbuf = nullptr;
     FC_CUDA(h, cudaFree(h->d_tc)); h->d_tc = nullptr;
+    FC_CUDA(h, cudaFree(h->d_tcsteps)); h->d_tcsteps = nullptr;
     FC_CUDA(h, cudaMalloc(&h->d_plans, sizeof(StepPlan) * T));
     FC_CUDA(h, cudaMalloc(&h->d_wbuf, buf.size() * sizeof(float)));
     FC_CUDA(h, cudaMemcpyAsync(h->d_plans, plans.data(), sizeof(StepPlan) * T, cudaMemcpyHostToDevice, stream));
@@ -253,6 +258,8 @@ extern "C" int fc_load_weights(fc_handle* h, const float* blob, size_t n_floats,
     if (h->tc_bytes) {
         FC_CUDA(h, cudaMalloc(&h->d_tc, h->tc_bytes));
         FC_CUDA(h, cudaMemcpyAsync(h->d_tc, tc_img.data(), h->tc_bytes, cudaMemcpyHostToDevice, stream));
+        FC_CUDA(h, cudaMalloc(&h->d_tcsteps, sizeof(fc::TcStep) * T));
+        FC_CUDA(h, cudaMemcpyAsync(h->d_tcsteps, tc_steps.data(), sizeof(fc::TcStep) * T, cudaMemcpyHostToDevice, stream));
     }
     FC_CUDA(h, cudaStreamSynchronize(stream));
     h->plans = plans;
@@ -294,7 +301,7 @@ int launch_density(fc_handle* h, RowArgs a, Mode mode, int precision, cudaStream
     if (precision == FC_PREC_BF16) {
         if (mode != MODE_SEPARATE) return fail(h, "the bf16 tensor-core path implements the per-step density only");
         std::string msg;
-        int rc = fc::tc_launch_separate(h->desc, h->d_plans, h->d_tc, h->tc_bytes, h->plans, a, h->num_sms, stream, &h->launches, &msg);
+        int rc = fc::tc_launch_separate(h->tcdims, h->d_tcsteps, h->d_tc, a, h->num_sms, h->smem_optin, stream, &h->launches, &msg);
         if (rc) return fail(h, "%s", msg.c_str());
         return 0;
     }
@@ -454,9 +461,9 @@ extern "C" int fc_update(fc_handle* h, const float* new_pos, int t, const float*
     return 0;
 }
 
-extern "C" int fc_tc_gemm_selftest(const float* A, const float* B, float* D, int N, int K, int device) {
+extern "C" int fc_tc_gemm_selftest(const float* A, const float* B, float* D, int N, int K, int device, int mode) {
     std::string msg;
-    int rc = fc::tc_selftest(A, B, D, N, K, device, &msg);
+    int rc = fc::tc_selftest(A, B, D, N, K, device, &msg, mode);
     if (rc) g_err = msg;
     return rc;
 }

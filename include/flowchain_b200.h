@@ -107,8 +107,9 @@ int fc_update(fc_handle* h, const float* new_pos, int time_step, const float* pr
 
 /* Diagnostic: D[128 x N] = A[128 x K] * B[N x K]^T on the tcgen05 tensor cores (bf16 operands, fp32
  * accumulate) through the same descriptor / TMEM / mbarrier helpers the fused kernel uses.  HOST pointers,
- * row-major fp32; N multiple of 16 in [16,256], K in [1,256].  Error text via fc_last_error(NULL). */
-int fc_tc_gemm_selftest(const float* A, const float* B, float* D, int N, int K, int device);
+ * row-major fp32; N multiple of 16 in [16,256], K in [1,256].  mode 0: bf16, A and B tiles in shared memory;
+ * mode 1: fp16, A operand resident in tensor memory (written with tcgen05.st).  Error text via fc_last_error(NULL). */
+int fc_tc_gemm_selftest(const float* A, const float* B, float* D, int N, int K, int device, int mode);
 
 /* Number of kernels this library has launched on behalf of `h` since creation (bench.py's gpu_launches). */
 uint64_t fc_launch_count(const fc_handle* h);

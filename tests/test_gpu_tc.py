@@ -15,8 +15,13 @@ def bf16_round(a):
     return t.to(torch.bfloat16).to(torch.float32).numpy()
 
 
+def f16_round(a):
+    return np.asarray(a, np.float32).astype(np.float16).astype(np.float32)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("N,K", [(16, 16), (64, 64), (128, 34), (160, 40), (80, 80), (48, 80), (256, 256), (32, 1)])
-def test_tcgen05_gemm_selftest(N, K):
+def test_tcgen05_gemm_selftest(N, K, mode):
     """D[128 x N] = A[128 x K] B[N x K]^T through the UMMA descriptors / TMEM / mbarrier helpers of the fused
     kernel; exact vs a float64 product of the bf16-rounded operands up to fp32 accumulation order."""
     lib = _lib.load()
@@ -24,7 +29,85 @@ def test_tcgen05_gemm_selftest(N, K):
     A = rng.standard_normal((128, K)).astype(np.float32)
     B = rng.standard_normal((N, K)).astype(np.float32)
     D = np.zeros((128, N), dtype=np.float32)
-    rc = lib.fc_tc_gemm_selftest(A.ctypes.data, B.ctypes.data, D.ctypes.data, N, K, 0)
+    rc = lib.fc_tc_gemm_selftest(A.ctypes.data, B.ctypes.data, D.ctypes.data, N, K, 0, mode)
     assert rc == 0, _lib.last_error(None)
-    ref = bf16_round(A).astype(np.float64) @ bf16_round(B).astype(np.float64).T
+    rnd = f16_round if mode == 1 else bf16_round
+    ref = rnd(A).astype(np.float64) @ rnd(B).astype(np.float64).T
     np.testing.assert_allclose(D, ref, atol=1e-4 * np.sqrt(K), rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused tensor-core density path
+# ------------------------------------------------------------------------------------------------
+from conftest import load_golden  # noqa: E402
+from oracle import flowchain_oracle as orc  # noqa: E402
+from flowchain_iccv2023_b200 import synth  # noqa: E402
+
+# bf16 operands carry 8 mantissa bits; the base term amplifies an error dw in the flow output by
+# |w - prev| / sigma^2 (sigma ~ 0.1, |w - prev| up to ~3 on the [-3,3]^2 lattice), so the bound is mixed:
+BF16_ATOL, BF16_RTOL = 5e-3, 2e-3
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(scope="module")
+def flow_default():
+    from flowchain_iccv2023_b200.flow import fastpredNF_CIF_separate_cond
+    spec, params, g = load_golden("default_eth")
+    f = fastpredNF_CIF_separate_cond(2, spec.n_blocks, spec.hidden_size, spec.n_hidden, spec.cond_size,
+                                     flow_architecture="realNVP", pred_len=spec.pred_len)
+    f.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+    return f.cuda().eval(), spec, params, g
+
+
+def report(name, out, ref):
+    err = np.abs(np.asarray(out, np.float64) - ref)
+    tol = BF16_ATOL + BF16_RTOL * np.abs(ref)
+    print(f"{name}: max|err| {err.max():.3e}  p50 {np.median(err):.3e}  p99 {np.quantile(err, 0.99):.3e}  "
+          f"max err/tol {np.max(err / tol):.3f}  max|ref| {np.abs(ref).max():.1f}")
+    return err, tol
+
+
+def test_tc_log_prob_golden(flow_default):
+    f, spec, p, g = flow_default
+    out = f.log_prob(T(g["base_pos"]), T(g["x"]), T(g["cond"]), eps=T(g["eps"]), precision=_lib.FC_PREC_BF16).cpu().numpy()
+    err, tol = report("tc log_prob", out, g["log_prob_64"])
+    assert np.all(err <= tol)
+
+
+def test_tc_grid_golden(flow_default):
+    f, spec, p, g = flow_default
+    out = f.grid_log_prob(T(g["base_pos"]), T(g["cond"]), T(g["grid"]), eps=T(g["eps_grid"]),
+                          precision=_lib.FC_PREC_BF16).cpu().numpy()
+    err, tol = report("tc grid self", out, g["grid_self_64"])
+    assert np.all(err <= tol)
+    out = f.grid_log_prob(T(g["base_pos"]), T(g["cond"]), T(g["grid"]), cond_traj=T(g["cond_traj"]), eps=T(g["eps_grid"]),
+                          precision=_lib.FC_PREC_BF16, map_layout=True).cpu().numpy()
+    err, tol = report("tc grid shared", out.transpose(0, 2, 1), g["grid_shared_64"])
+    assert np.all(err <= tol)
+
+
+def test_tc_ragged_rows_vs_oracle(flow_default):
+    f, spec, p, g = flow_default
+    for N in (1, 127, 129, 385):
+        inp = synth.make_inputs(spec, N, seed=500 + N)
+        x = (inp["base_pos"][:, None, :] + 0.5 * synth.normal(600 + N, "x", (N, spec.pred_len, 2))).astype(np.float32)
+        eps = synth.make_eps(spec, N, 700 + N)
+        ref = orc.log_prob(p, inp["base_pos"], x, inp["cond"], eps, np.float64)
+        out = f.log_prob(T(inp["base_pos"]), T(x), T(inp["cond"]), eps=T(eps), precision=_lib.FC_PREC_BF16).cpu().numpy()
+        err, tol = report(f"tc ragged N={N}", out, ref)
+        assert np.all(err <= tol)
+
+
+def test_tc_matches_fp32_path_at_scale(flow_default):
+    """Same in-kernel Philox stream in both paths: 8 agents x 64x64 lattice, bf16 vs fp32 kernels."""
+    f, spec, p, g = flow_default
+    inp = synth.make_inputs(spec, 8, seed=11)
+    grid = synth.make_grid(64)
+    a32 = f.grid_log_prob(T(inp["base_pos"]), T(inp["cond"]), T(grid), seed=3, precision=_lib.FC_PREC_FP32).cpu().numpy()
+    a16 = f.grid_log_prob(T(inp["base_pos"]), T(inp["cond"]), T(grid), seed=3, precision=_lib.FC_PREC_BF16).cpu().numpy()
+    err, tol = report("tc vs fp32 (philox)", a16, a32.astype(np.float64))
+    assert np.all(np.isfinite(a16))
+    assert np.mean(err <= tol) > 0.999
