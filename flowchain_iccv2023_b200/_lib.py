@@ -10,10 +10,12 @@ import os
 from ctypes import POINTER, c_char_p, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libflowchain_b200.so")
+LIB_PATH = os.environ.get("FLOWCHAIN_B200_LIB", os.path.join(_HERE, "libflowchain_b200.so"))
 
 FC_PREC_FP32 = 0
 FC_PREC_BF16 = 1
+FC_PREC_F16X3 = 2
+FC_PREC_F16 = 3
 FC_PREFIX_SELF = 0
 FC_PREFIX_SHARED = 1
 

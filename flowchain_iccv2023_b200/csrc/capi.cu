@@ -12,8 +12,12 @@
 #include "../../include/flowchain_b200.h"
 #include "kernels_fp32.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_tc2.cuh"
 #include "plan.h"
 
+#ifndef FC_T2_PARTS
+#define FC_T2_PARTS 2
+#endif
 using namespace fc;
 
 struct fc_handle {
@@ -31,6 +35,10 @@ struct fc_handle {
     size_t tc_bytes = 0;
     fc::TcStep* d_tcsteps = nullptr;
     fc::TcDims tcdims{};
+    // accurate tensor-core path: [0] = 3-pass split fp16 (f16x3), [1] = single-pass fp16
+    unsigned char* d_t2img[2] = {nullptr, nullptr};
+    fc::T2Step* d_t2steps[2] = {nullptr, nullptr};
+    fc::T2Dims t2dims[2]{};
     float* d_scratch = nullptr;       // K>1 importance-sample staging
     size_t scratch_floats = 0;
     Dims dims{};
@@ -111,6 +119,7 @@ extern "C" void fc_destroy(fc_handle* h) {
     cudaFree(h->d_wbuf);
     cudaFree(h->d_tc);
     cudaFree(h->d_tcsteps);
+    for (int i = 0; i < 2; ++i) { cudaFree(h->d_t2img[i]); cudaFree(h->d_t2steps[i]); }
     cudaFree(h->d_scratch);
     delete h;
 }
@@ -261,6 +270,19 @@ extern "C" int fc_load_weights(fc_handle* h, const float* blob, size_t n_floats,
         FC_CUDA(h, cudaMalloc(&h->d_tcsteps, sizeof(fc::TcStep) * T));
         FC_CUDA(h, cudaMemcpyAsync(h->d_tcsteps, tc_steps.data(), sizeof(fc::TcStep) * T, cudaMemcpyHostToDevice, stream));
     }
+    for (int i = 0; i < 2; ++i) {
+        std::vector<unsigned char> img2;
+        std::vector<fc::T2Step> st2;
+        fc::tc2_pack(d, plans, tcsrc, i == 0 ? 3 : 1, img2, st2, h->t2dims[i], h->smem_optin);
+        FC_CUDA(h, cudaFree(h->d_t2img[i])); h->d_t2img[i] = nullptr;
+        FC_CUDA(h, cudaFree(h->d_t2steps[i])); h->d_t2steps[i] = nullptr;
+        if (h->t2dims[i].supported) {
+            FC_CUDA(h, cudaMalloc(&h->d_t2img[i], img2.size()));
+            FC_CUDA(h, cudaMemcpy(h->d_t2img[i], img2.data(), img2.size(), cudaMemcpyHostToDevice));
+            FC_CUDA(h, cudaMalloc(&h->d_t2steps[i], sizeof(fc::T2Step) * T));
+            FC_CUDA(h, cudaMemcpy(h->d_t2steps[i], st2.data(), sizeof(fc::T2Step) * T, cudaMemcpyHostToDevice));
+        }
+    }
     FC_CUDA(h, cudaStreamSynchronize(stream));
     h->plans = plans;
     h->wbuf_floats = buf.size();
@@ -302,6 +324,15 @@ int launch_density(fc_handle* h, RowArgs a, Mode mode, int precision, cudaStream
         if (mode != MODE_SEPARATE) return fail(h, "the bf16 tensor-core path implements the per-step density only");
         std::string msg;
         int rc = fc::tc_launch_separate(h->tcdims, h->d_tcsteps, h->d_tc, a, h->num_sms, h->smem_optin, stream, &h->launches, &msg);
+        if (rc) return fail(h, "%s", msg.c_str());
+        return 0;
+    }
+    if (precision == FC_PREC_F16X3 || precision == FC_PREC_F16) {
+        if (mode != MODE_SEPARATE) return fail(h, "the tensor-core path implements the per-step density only");
+        std::string msg;
+        const int i = precision == FC_PREC_F16X3 ? 0 : 1;
+        int rc = i == 0 ? fc::tc2_launch_separate<3, FC_T2_PARTS>(h->t2dims[0], h->d_t2steps[0], h->d_t2img[0], a, h->num_sms, h->smem_optin, stream, &h->launches, &msg)
+                        : fc::tc2_launch_separate<1, FC_T2_PARTS>(h->t2dims[1], h->d_t2steps[1], h->d_t2img[1], a, h->num_sms, h->smem_optin, stream, &h->launches, &msg);
         if (rc) return fail(h, "%s", msg.c_str());
         return 0;
     }

@@ -49,7 +49,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
     return ctr;
 }
 
-__device__ __forceinline__ float4 philox_normal4(unsigned long long seed, long long row, unsigned key, unsigned blk) {
+__device__ __noinline__ float4 philox_normal4(unsigned long long seed, long long row, unsigned key, unsigned blk) {
     const uint4 r = philox4x32_10(make_uint4((unsigned)row, (unsigned)((unsigned long long)row >> 32), key, blk),
                                   make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
     const float u0 = ((r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);

@@ -43,8 +43,11 @@ typedef struct fc_model_desc {
 } fc_model_desc;
 
 /* arithmetic path of the conditioner / auxiliary-density MLPs */
-enum { FC_PREC_FP32 = 0,   /* CUDA-core fp32, parity 1e-4 (+rel) nats                         */
-       FC_PREC_BF16 = 1 }; /* tcgen05 tensor cores, bf16 operands / fp32 accumulate, 5e-3 (+rel) */
+enum { FC_PREC_FP32 = 0,    /* CUDA-core fp32, parity 1e-4 (+rel) nats                                         */
+       FC_PREC_BF16 = 1,    /* tcgen05, bf16 operands / fp32 accumulate, single pass: fast, ~1e-1 nats           */
+       FC_PREC_F16X3 = 2,   /* tcgen05, split-fp16 operands (a_hi+a_lo)(W_hi+W_lo), 3 MMA passes, fp32 accumulate:
+                               fp32-grade, meets the 5e-3 nats tensor-core parity bar                             */
+       FC_PREC_F16 = 3 };   /* tcgen05, fp16 operands / fp32 accumulate, single pass: ~3e-2 nats                  */
 
 /* prefix modes of the dense-grid evaluation */
 enum { FC_PREFIX_SELF = 0,     /* x[:, i] = g for every step (the literal reference call)   */

@@ -43,9 +43,16 @@ from conftest import load_golden  # noqa: E402
 from oracle import flowchain_oracle as orc  # noqa: E402
 from flowchain_iccv2023_b200 import synth  # noqa: E402
 
-# bf16 operands carry 8 mantissa bits; the base term amplifies an error dw in the flow output by
-# |w - prev| / sigma^2 (sigma ~ 0.1, |w - prev| up to ~3 on the [-3,3]^2 lattice), so the bound is mixed:
-BF16_ATOL, BF16_RTOL = 5e-3, 2e-3
+# Tolerances against the fp64 oracle, |d| <= atol + rtol*|ref64| nats:
+#   f16x3 (split-fp16, 3 MMA passes)  : the north_star tensor-core bar, 5e-3 nats (+ the fp32 relative floor 3e-6)
+#   f16 / bf16 (single pass)          : fast approximate modes.  Operand rounding (2^-11 / 2^-8) is amplified by
+#                                       |w - prev| / sigma^2 in the base term (sigma ~ 0.1), so their error is a
+#                                       few 1e-2 / 1e-1 nats on the [-3,3]^2 lattice; the bound below documents it.
+MODES = {
+    "f16x3": (_lib.FC_PREC_F16X3, 5e-3, 3e-6),
+    "f16": (_lib.FC_PREC_F16, 0.05, 1e-3),
+    "bf16": (_lib.FC_PREC_BF16, 0.5, 1e-2),
+}
 
 
 def T(a):
@@ -62,52 +69,63 @@ def flow_default():
     return f.cuda().eval(), spec, params, g
 
 
-def report(name, out, ref):
+def check(name, out, ref, mode, frac=1.0):
+    _, atol, rtol = MODES[mode]
     err = np.abs(np.asarray(out, np.float64) - ref)
-    tol = BF16_ATOL + BF16_RTOL * np.abs(ref)
-    print(f"{name}: max|err| {err.max():.3e}  p50 {np.median(err):.3e}  p99 {np.quantile(err, 0.99):.3e}  "
+    tol = atol + rtol * np.abs(ref)
+    print(f"[{mode}] {name}: max|err| {err.max():.3e}  p50 {np.median(err):.3e}  p99 {np.quantile(err, 0.99):.3e}  "
           f"max err/tol {np.max(err / tol):.3f}  max|ref| {np.abs(ref).max():.1f}")
-    return err, tol
+    assert np.all(np.isfinite(out))
+    assert np.mean(err <= tol) >= frac, f"{name}: {np.mean(err <= tol):.5f} of values within tolerance"
 
 
-def test_tc_log_prob_golden(flow_default):
+@pytest.mark.parametrize("mode", list(MODES))
+def test_tc_log_prob_golden(flow_default, mode):
     f, spec, p, g = flow_default
-    out = f.log_prob(T(g["base_pos"]), T(g["x"]), T(g["cond"]), eps=T(g["eps"]), precision=_lib.FC_PREC_BF16).cpu().numpy()
-    err, tol = report("tc log_prob", out, g["log_prob_64"])
-    assert np.all(err <= tol)
+    out = f.log_prob(T(g["base_pos"]), T(g["x"]), T(g["cond"]), eps=T(g["eps"]), precision=MODES[mode][0]).cpu().numpy()
+    check("log_prob", out, g["log_prob_64"], mode)
 
 
-def test_tc_grid_golden(flow_default):
+@pytest.mark.parametrize("mode", list(MODES))
+def test_tc_grid_golden(flow_default, mode):
     f, spec, p, g = flow_default
     out = f.grid_log_prob(T(g["base_pos"]), T(g["cond"]), T(g["grid"]), eps=T(g["eps_grid"]),
-                          precision=_lib.FC_PREC_BF16).cpu().numpy()
-    err, tol = report("tc grid self", out, g["grid_self_64"])
-    assert np.all(err <= tol)
+                          precision=MODES[mode][0]).cpu().numpy()
+    check("grid self", out, g["grid_self_64"], mode)
     out = f.grid_log_prob(T(g["base_pos"]), T(g["cond"]), T(g["grid"]), cond_traj=T(g["cond_traj"]), eps=T(g["eps_grid"]),
-                          precision=_lib.FC_PREC_BF16, map_layout=True).cpu().numpy()
-    err, tol = report("tc grid shared", out.transpose(0, 2, 1), g["grid_shared_64"])
-    assert np.all(err <= tol)
+                          precision=MODES[mode][0], map_layout=True).cpu().numpy()
+    check("grid shared", out.transpose(0, 2, 1), g["grid_shared_64"], mode)
 
 
-def test_tc_ragged_rows_vs_oracle(flow_default):
+@pytest.mark.parametrize("mode", list(MODES))
+def test_tc_ragged_rows_vs_oracle(flow_default, mode):
     f, spec, p, g = flow_default
     for N in (1, 127, 129, 385):
         inp = synth.make_inputs(spec, N, seed=500 + N)
         x = (inp["base_pos"][:, None, :] + 0.5 * synth.normal(600 + N, "x", (N, spec.pred_len, 2))).astype(np.float32)
         eps = synth.make_eps(spec, N, 700 + N)
         ref = orc.log_prob(p, inp["base_pos"], x, inp["cond"], eps, np.float64)
-        out = f.log_prob(T(inp["base_pos"]), T(x), T(inp["cond"]), eps=T(eps), precision=_lib.FC_PREC_BF16).cpu().numpy()
-        err, tol = report(f"tc ragged N={N}", out, ref)
-        assert np.all(err <= tol)
+        out = f.log_prob(T(inp["base_pos"]), T(x), T(inp["cond"]), eps=T(eps), precision=MODES[mode][0]).cpu().numpy()
+        check(f"ragged N={N}", out, ref, mode)
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+def test_tc_config1_lattice_vs_oracle(flow_default, mode):
+    """Config 1 shape (1 agent x 100x100 lattice x 12 steps) against the fp64 oracle with an injected tape."""
+    f, spec, p, g = flow_default
+    inp = synth.make_inputs(spec, 1, seed=7)
+    grid = synth.make_grid(100)
+    eps = synth.make_eps(spec, grid.shape[0], 8)
+    ref = orc.grid_log_prob_self(p, inp["base_pos"], inp["cond"], grid, eps, np.float64)
+    out = f.grid_log_prob(T(inp["base_pos"]), T(inp["cond"]), T(grid), eps=T(eps), precision=MODES[mode][0]).cpu().numpy()
+    check("config1 self", out, ref, mode, frac=1.0 if mode == "f16x3" else 0.995)
 
 
 def test_tc_matches_fp32_path_at_scale(flow_default):
-    """Same in-kernel Philox stream in both paths: 8 agents x 64x64 lattice, bf16 vs fp32 kernels."""
+    """Same in-kernel Philox stream in both paths: 8 agents x 128x128 lattice, f16x3 tensor-core vs fp32 CUDA-core."""
     f, spec, p, g = flow_default
     inp = synth.make_inputs(spec, 8, seed=11)
-    grid = synth.make_grid(64)
+    grid = synth.make_grid(128)
     a32 = f.grid_log_prob(T(inp["base_pos"]), T(inp["cond"]), T(grid), seed=3, precision=_lib.FC_PREC_FP32).cpu().numpy()
-    a16 = f.grid_log_prob(T(inp["base_pos"]), T(inp["cond"]), T(grid), seed=3, precision=_lib.FC_PREC_BF16).cpu().numpy()
-    err, tol = report("tc vs fp32 (philox)", a16, a32.astype(np.float64))
-    assert np.all(np.isfinite(a16))
-    assert np.mean(err <= tol) > 0.999
+    a16 = f.grid_log_prob(T(inp["base_pos"]), T(inp["cond"]), T(grid), seed=3, precision=_lib.FC_PREC_F16X3).cpu().numpy()
+    check("f16x3 vs fp32 kernels (philox)", a16, a32.astype(np.float64), "f16x3")
