@@ -498,3 +498,13 @@ extern "C" int fc_tc_gemm_selftest(const float* A, const float* B, float* D, int
     if (rc) g_err = msg;
     return rc;
 }
+
+// development aid: per-phase cycle counters of the tensor-core kernel (only filled when built with -DFC_T2_PROF=1)
+extern "C" int fc_debug_t2prof(unsigned long long* out16, int reset) {
+    if (out16 && cudaMemcpyFromSymbol(out16, fc::g_t2prof, sizeof(unsigned long long) * 16) != cudaSuccess) return 1;
+    if (reset) {
+        unsigned long long z[16] = {0};
+        if (cudaMemcpyToSymbol(fc::g_t2prof, z, sizeof z) != cudaSuccess) return 1;
+    }
+    return 0;
+}

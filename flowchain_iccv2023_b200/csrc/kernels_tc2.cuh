@@ -40,6 +40,11 @@ struct T2Step {
     int32_t masked_dim[kMaxBlocks];
     float bn_scale[kMaxBlocks][2], bn_shift[kMaxBlocks][2], bn_ldj[kMaxBlocks];
     float std[2];
+    // MMA-issuer schedule, one entry per chunk (= net-layer), executed in order:
+    //   wait on barrier `wait` (0 none, 1 opnd[0], 2 opnd[1], 3 fin) -> issue the MMAs -> hand back `rel` older chunks
+    uint8_t job_wait[kT2MaxChunks], job_rel[kT2MaxChunks], job_net[kT2MaxChunks], job_src[kT2MaxChunks];  // src: 0 IN, 1 U, 2 H[net]
+    uint8_t job_kp[kT2MaxChunks], job_n[kT2MaxChunks];      // Kp, N in elements
+    uint8_t tail_rel, pad1[3];                                // chunks handed back after the last `fin`
 };
 
 struct T2Dims {
@@ -120,13 +125,48 @@ inline void tc2_pack(const fc_model_desc& d, const std::vector<StepPlan>& plans,
         }
         dens(1);
         ts.nchunks = nch;
+        {   // issuer schedule (see k_separate_tc2: compute warps arrive on fin / opnd[net] in exactly this order)
+            int j = 0;
+            auto put = [&](int wait, int net, int src_, int kp, int n, int rel) {
+                ts.job_wait[j] = (uint8_t)wait; ts.job_net[j] = (uint8_t)net; ts.job_src[j] = (uint8_t)src_;
+                ts.job_kp[j] = (uint8_t)kp; ts.job_n[j] = (uint8_t)n; ts.job_rel[j] = (uint8_t)rel; ++j;
+            };
+            auto density = [&](bool first) {
+                // L1 of both nets reads the input operand; `fin` was awaited by the caller's first entry
+                put(3, 0, 0, ts.Kin, ts.Wd, 0);
+                put(0, 1, 0, ts.Kin, ts.Wd, first ? 0 : 2);          // q: hand back the last block's last-layer chunks
+                for (int l = 0; l < 2; ++l)
+                    for (int net = 0; net < 2; ++net) put(1 + net, net, 2, ts.Wd, l == 0 ? ts.Wd : ts.CPd, 1);
+            };
+            density(true);
+            for (int b = 0; b < sp.n_blocks; ++b) {
+                put(3, 0, 1, ts.Ku, H, 0);
+                put(0, 1, 1, ts.Ku, H, 2);                            // L3 chunks of r / last-layer chunks of block b-1
+                for (int l = 0; l < sp.n_hidden; ++l)
+                    for (int net = 0; net < 2; ++net) put(1 + net, net, 2, H, H, 1);
+            }
+            density(false);
+            ts.tail_rel = 2;                                          // the q density's two L3 chunks (after the last fin)
+        }
     }
     while (img.size() % 128) img.push_back(0);
     dm.slot_bytes = (dm.slot_bytes + 127) / 128 * 128;
-    dm.nslots = (smem_optin - 9728) / dm.slot_bytes;
+    dm.nslots = (smem_optin - 10240) / dm.slot_bytes;
     if (dm.nslots > 12) dm.nslots = 12;
     dm.supported = dm.nslots >= 3;
 }
+
+#ifndef FC_T2_PROF
+#define FC_T2_PROF 0
+#endif
+__device__ unsigned long long g_t2prof[16];
+#define T2_TICK(i)                                                                      \
+    if (FC_T2_PROF && blockIdx.x == 0 && threadIdx.x == 0) {                            \
+        long long now_;                                                                 \
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(now_));                            \
+        atomicAdd(&g_t2prof[i], (unsigned long long)(now_ - prof_t));                   \
+        prof_t = now_;                                                                  \
+    }
 
 namespace t2 {
 using namespace tc;
@@ -157,7 +197,10 @@ __device__ __forceinline__ void split8(const float* a, uint32_t* hi, uint32_t* l
         }
     }
 }
-__device__ __forceinline__ float tanh_acc(float x) {   // |err| ~ 5e-7: ex2.approx + fast divide, no MUFU.TANH (2^-11)
+// tanh(x) = 1 - 2 / (1 + e^{2x}), |err| ~ 5e-7 (MUFU.TANH itself is only 2^-11 accurate).  Two MUFU ops (ex2, rcp) and
+// four FMA-pipe ops per value; an FMA-pipe Newton reciprocal was measured slower (the FP32 pipe, not MUFU, is the
+// scarcer resource in these epilogues).
+__device__ __forceinline__ float tanh_acc(float x) {
     float e;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
     return 1.0f - __fdividef(2.0f, e + 1.0f);
@@ -167,11 +210,8 @@ __device__ __forceinline__ float tanh_acc(float x) {   // |err| ~ 5e-7: ex2.appr
 struct Bars {
     uint64_t full[12], empty[12];    // weight ring: producer <-> MMA warp
     uint64_t mma_done[2];            // tcgen05.commit of the newest layer of net 0 / 1
-    // arrival counters (monotonic): the LAST compute warp to finish a stage issues the next MMAs itself --
-    // no issuer-warp wake-up in the dependency chain
-    uint32_t cnt_opnd[2];            // epilogue of net 0 / 1 finished (its next operand is in tensor memory)
-    uint32_t cnt_fin;                // a sub-network finished (input operand of the next one is ready)
-    uint32_t pad;
+    uint64_t opnd[2];                // all compute warps finished the epilogue of net 0 / 1 (its next operand is in TMEM)
+    uint64_t fin;                    // all compute warps finished a sub-network (input operand of the next one is ready)
 };
 
 struct X {
@@ -194,26 +234,13 @@ __device__ __forceinline__ void wait_mma(X& x, int net) {
     else { mbar_wait(&x.bars->mma_done[1], x.mma_cnt1 & 1u); x.mma_cnt1++; }
     tc_fence_after();
 }
-// A compute warp finished a stage (its tensor-memory reads/writes are complete).  Returns true -- in all lanes --
-// for the LAST of the NCW warps: that warp then issues the dependent MMAs / hands weight slots back.
-template <int NCW>
-__device__ __forceinline__ bool arrive_last(const X& x, uint32_t* cnt) {
+// a compute warp tells the MMA warp that its tensor-memory reads/writes for this stage are complete
+__device__ __forceinline__ void warp_arrive(const X& x, uint64_t* bar) {
     tmem_wait_ld();
     tmem_wait_st();
     tc_fence_before();
     __syncwarp();
-    unsigned old = 0;
-    if (x.lane == 0) {
-        __threadfence_block();
-        old = atomicAdd(cnt, 1u);
-    }
-    old = __shfl_sync(0xffffffffu, old, 0);
-    const bool last = (old % NCW) == NCW - 1;
-    if (last) {
-        __threadfence_block();
-        tc_fence_after();
-    }
-    return last;
+    if (x.lane == 0) mbar_arrive(bar);
 }
 
 enum { ACT_R = 0, ACT_T = 1 };
@@ -305,53 +332,48 @@ __device__ __noinline__ void mma_issue(Bars* bars, const uint8_t* chunk, uint32_
     const uint32_t acc = tb0 + (net ? kT2Acc1 : kT2Acc0);
     const uint64_t dhi = umma_desc(b_hi, 128, sbo), dlo = umma_desc(b_lo, 128, sbo);
     const int nk = (FC_T2_ABLATE & 2) ? 0 : (Kp >> 4);
+#pragma unroll 1
     for (int ks = 0; ks < nk; ++ks) umma_ts_elect(acc, tb0 + a_hi + ks * 8, dhi + (uint64_t)(ks * 16), idesc, ks > 0 ? 1u : 0u);
     if (NPASS == 3) {
+#pragma unroll 1
         for (int ks = 0; ks < nk; ++ks) umma_ts_elect(acc, tb0 + a_lo + ks * 8, dhi + (uint64_t)(ks * 16), idesc, 1u);
+#pragma unroll 1
         for (int ks = 0; ks < nk; ++ks) umma_ts_elect(acc, tb0 + a_hi + ks * 8, dlo + (uint64_t)(ks * 16), idesc, 1u);
     }
     umma_commit_elect(&bars->mma_done[net]);
 }
 
-// issuing warp only (convergent): next weight chunk -> MMAs of one net-layer -> commit
-template <int NPASS>
-__device__ __forceinline__ void job(const X& x, uint32_t it, int net, uint32_t a_hi, uint32_t a_lo, int Kp, int N) {
-    wait_full(x, it);
-    tc_fence_after();
-    mma_issue<NPASS>(x.bars, slot_ptr(x, it), x.tb0, net, a_hi, a_lo, Kp, N);
-}
-__device__ __forceinline__ void release(const X& x, uint32_t it) { mbar_arrive_elect(&x.bars->empty[it % x.nslots]); }
-
 }  // namespace t2
 
-// Warp roles: [0, 4*NPARTS) compute (warp w: lane quadrant w % 4, column part w / 4) + one weight-producer warp (TMA).
-// No CTA-wide barrier inside an item.  The dependency chain of a net is  epilogue(l) -> MMA(l+1) -> epilogue(l+1):
-// the compute warp that finishes epilogue(l) LAST issues MMA(l+1) itself (arrival counter in shared memory), the
-// MMA completion comes back through an mbarrier (tcgen05.commit).
+// Warp roles: [0, 4*NPARTS) compute (warp w: lane quadrant w % 4, column part w / 4), then the weight producer (TMA)
+// and the MMA issuer.  No CTA-wide barrier inside an item: roles hand work to each other through mbarriers only
+// (epilogue(l) -> `opnd` -> MMA(l+1) -> tcgen05.commit -> `mma_done` -> epilogue(l+1)).
 template <int NPASS, int NPARTS>
-__global__ void __launch_bounds__(NPARTS * 128 + 32, 1)
+__global__ void __launch_bounds__(NPARTS * 128 + 64, 1)
 k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img, RowArgs a, T2Dims dm, long long tiles_per_step,
                long long total_items) {
     using namespace tc;
     using namespace t2;
     constexpr int NCW = 4 * NPARTS;                  // compute warps
-    constexpr int kThreadsAll = NPARTS * 128 + 32;
+    constexpr int kThreadsAll = NPARTS * 128 + 64;
     extern __shared__ __align__(128) uint8_t smem_t2[];
     uint8_t* smem = smem_t2;
     Bars* bars = reinterpret_cast<Bars*>(smem);
     static_assert(sizeof(Bars) <= 240, "barrier block");
     uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + 240);
     T2Step* cur = reinterpret_cast<T2Step*>(smem + 256);
-    static_assert(sizeof(T2Step) <= 1280, "T2Step must fit the header");
-    float* part = reinterpret_cast<float*>(smem + 1536);         // 4 x NPARTS x 128 floats (<= 8 KB) -> header is 9728 B
-    uint8_t* slots = smem + 9728;
+    static_assert(sizeof(T2Step) <= 1792, "T2Step must fit the header");
+    float* part = reinterpret_cast<float*>(smem + 2048);         // 4 x NPARTS x 128 floats (<= 8 KB) -> header is 10240 B
+    uint8_t* slots = smem + 10240;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < dm.nslots; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
         mbar_init(&bars->mma_done[0], 1);
         mbar_init(&bars->mma_done[1], 1);
-        bars->cnt_opnd[0] = 0; bars->cnt_opnd[1] = 0; bars->cnt_fin = 0;
+        mbar_init(&bars->opnd[0], NCW);
+        mbar_init(&bars->opnd[1], NCW);
+        mbar_init(&bars->fin, NCW);
         mbar_fence_init();
     }
     if (warp == NCW) tmem_alloc(tslot, 512);
@@ -366,11 +388,15 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
     x.tb = x.tb0 + ((uint32_t)((warp & 3) * 32) << 16);
     x.bars = bars; x.slots = slots; x.slot_bytes = dm.slot_bytes; x.nslots = dm.nslots;
     x.chunk_it = 0; x.issue_it = 0; x.rel_it = 0; x.mma_cnt0 = 0; x.mma_cnt1 = 0; x.part_buf = part;
-    uint32_t ring_it = 0;            // producer ring position
+    uint32_t ring_it = 0;            // producer / MMA-warp ring position
+    uint32_t opnd_cnt0 = 0, opnd_cnt1 = 0, fin_cnt = 0;
 
+    long long prof_t = 0;
+    if (FC_T2_PROF) asm volatile("mov.u64 %0, %%clock64;" : "=l"(prof_t));
     for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
         const int step = dm.T - 1 - (int)(item / tiles_per_step);      // heavy (late) steps first
         const long long tile = item % tiles_per_step;
+        T2_TICK(0)   // tail of previous item (output store)
         __syncthreads();
         {
             const int nw = sizeof(T2Step) / 4;
@@ -399,7 +425,33 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
             continue;
         }
 
+        if (warp == NCW + 1) {
+            // ===== MMA issuer (whole warp convergent, one elected lane issues): runs the step's job table.  A stage's
+            // weight chunk is handed back AFTER the dependent MMAs are issued: the release is off the critical path. =====
+            uint32_t rel = ring_it;
+#pragma unroll 1
+            for (int ci = 0; ci < ts.nchunks; ++ci, ++ring_it) {
+                const int w = ts.job_wait[ci], net = ts.job_net[ci], src = ts.job_src[ci];
+                if (w == 1) { mbar_wait(&bars->opnd[0], opnd_cnt0 & 1u); opnd_cnt0++; }
+                else if (w == 2) { mbar_wait(&bars->opnd[1], opnd_cnt1 & 1u); opnd_cnt1++; }
+                else if (w == 3) { mbar_wait(&bars->fin, fin_cnt & 1u); fin_cnt++; }
+                mbar_wait(&bars->full[ring_it % dm.nslots], (ring_it / dm.nslots) & 1u);
+                tc_fence_after();
+                const uint32_t a_hi = src == 0 ? kT2InHi : (src == 1 ? kT2UHi : (net ? kT2H1Hi : kT2H0Hi));
+                const uint32_t a_lo = src == 0 ? kT2InLo : (src == 1 ? kT2ULo : (net ? kT2H1Lo : kT2H0Lo));
+                mma_issue<NPASS>(bars, slots + (size_t)(ring_it % dm.nslots) * dm.slot_bytes, x.tb0, net, a_hi, a_lo, ts.job_kp[ci], ts.job_n[ci]);
+#pragma unroll 1
+                for (int r = 0; r < ts.job_rel[ci]; ++r, ++rel) mbar_arrive_elect(&bars->empty[rel % dm.nslots]);
+            }
+            mbar_wait(&bars->fin, fin_cnt & 1u);                     // final q-density epilogue done
+            fin_cnt++;
+#pragma unroll 1
+            for (int r = 0; r < ts.tail_rel; ++r, ++rel) mbar_arrive_elect(&bars->empty[rel % dm.nslots]);
+            continue;
+        }
+
         // ===== compute warps: thread = (row, column part) =====
+        T2_TICK(1)   // item prologue: syncs + step table
         long long n = tile * 128 + x.row;
         const bool valid = n < a.N;
         if (!valid) n = a.N - 1;
@@ -431,12 +483,9 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
                 if (NPASS == 3) tmem_st4(x.tb + kT2InLo + (uint32_t)(k0 >> 1), lo);
             }
         }
+        T2_TICK(2)   // row setup + input gather
         // first sub-network: both r-density nets read the input operand
-        if (arrive_last<NCW>(x, &bars->cnt_fin)) {
-            job<NPASS>(x, x.issue_it, 0, kT2InHi, kT2InLo, Kin, Wd);
-            job<NPASS>(x, x.issue_it + 1, 1, kT2InHi, kT2InLo, Kin, Wd);
-        }
-        x.issue_it += 2;
+        warp_arrive(x, &bars->fin);
 
 #pragma unroll 1
         for (int which = 0; which < 2; ++which) {
@@ -448,13 +497,11 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
                     const uint32_t bias = smem_u32(slot_ptr(x, x.chunk_it)) + (uint32_t)((NPASS == 3 ? 2 : 1) * Wd * (l == 0 ? Kin : Wd) * 2);
                     wait_mma(x, net);        // (the issuing warp acquired the weight chunk; the commit orders it for us)
                     epi_hidden<NPASS, NPARTS, ACT_R, false, true>(x, net, Wd, bias, 0u);
-                    if (arrive_last<NCW>(x, &bars->cnt_opnd[net])) {
-                        release(x, x.rel_it);
-                        job<NPASS>(x, x.issue_it, net, net ? kT2H1Hi : kT2H0Hi, net ? kT2H1Lo : kT2H0Lo, Wd, l == 0 ? Wd : CPd);
-                    }
-                    x.rel_it++; x.issue_it++; x.chunk_it++;
+                    warp_arrive(x, &bars->opnd[net]);
+                    x.chunk_it++;
                 }
             }
+            T2_TICK(3 + which * 4)   // density hidden layers (3: r, 7: q)
             // ---- L3 outputs: means in acc0[0,CPd), log-stddevs in acc1[0,CPd) ----
             const size_t w3 = (size_t)(NPASS == 3 ? 2 : 1) * CPd * Wd * 2;
             const float* bias_mu = reinterpret_cast<const float*>(slot_ptr(x, x.chunk_it) + w3);
@@ -462,6 +509,7 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
             x.chunk_it += 2;
             wait_mma(x, 0);
             wait_mma(x, 1);
+            T2_TICK(4 + which * 4)   // wait for L3 MMAs (4: r, 8: q)
             if (which == 0) {
                 // sample u = exp(ls) eps + mu (fastpredNF.py:727-733) -> [u, mx] operand; log r = -C/2 log 2pi - sum ls - 1/2 sum eps^2
                 const int m0 = ts.masked_dim[0];
@@ -535,18 +583,10 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
                 const float s_ls = row_sum<NPARTS>(x, 0, p_ls), s_q = row_sum<NPARTS>(x, 1, p_q);
                 lacc += (-0.5f * (float)C * kLog2Pi - s_ls) - 0.5f * s_q;
             }
+            T2_TICK(5 + which * 4)   // final density epilogue E2 / E3 (5: r, 9: q)
             // end of the density sub-network: its two L3 chunks go back; after r the first coupling starts
-            if (arrive_last<NCW>(x, &bars->cnt_fin)) {
-                release(x, x.rel_it);
-                release(x, x.rel_it + 1);
-                if (which == 0) {
-                    job<NPASS>(x, x.issue_it, 0, kT2UHi, kT2ULo, Ku, Hc);
-                    job<NPASS>(x, x.issue_it + 1, 1, kT2UHi, kT2ULo, Ku, Hc);
-                }
-            }
-            x.rel_it += 2;
+            warp_arrive(x, &bars->fin);
             if (which == 1) break;
-            x.issue_it += 2;
 
             // ============ n_blocks x (masked affine coupling + BatchNorm), forward ============
 #pragma unroll 1
@@ -560,21 +600,22 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
                     for (int net = 0; net < 2; ++net) {
                         const uint32_t tail = smem_u32(slot_ptr(x, x.chunk_it)) + (uint32_t)((NPASS == 3 ? 2 : 1) * Hc * (l == 0 ? Ku : Hc) * 2);
                         x.chunk_it++;
+                        T2_TICK(6)
                         wait_mma(x, net);
+                        T2_TICK(12 + net)   // wait for the MMA of (l, net)
                         if (!last) {
                             if (net == 0) epi_hidden<NPASS, NPARTS, ACT_T, false, true>(x, 0, Hc, tail, 0u);
                             else epi_hidden<NPASS, NPARTS, ACT_R, false, true>(x, 1, Hc, tail, 0u);
-                            if (arrive_last<NCW>(x, &bars->cnt_opnd[net])) {
-                                release(x, x.rel_it);
-                                job<NPASS>(x, x.issue_it, net, net ? kT2H1Hi : kT2H0Hi, net ? kT2H1Lo : kT2H0Lo, Hc, Hc);
-                            }
-                            x.rel_it++; x.issue_it++;
+                            T2_TICK(14)     // epilogue math
+                            warp_arrive(x, &bars->opnd[net]);
+                            T2_TICK(15)     // arrive
                         } else {
                             if (net == 0) { ps = epi_hidden<NPASS, NPARTS, ACT_T, true, false>(x, 0, Hc, tail, tail + Hc * 4); bs = lds32(tail + Hc * 8); }
                             else { pt_ = epi_hidden<NPASS, NPARTS, ACT_R, true, false>(x, 1, Hc, tail, tail + Hc * 4); bt = lds32(tail + Hc * 8); }
                         }
                     }
                 }
+                T2_TICK(6)   // coupling layers (all blocks)
                 // both nets done: affine update of the unmasked coordinate + BatchNorm (TFCondARFlow.py:360-381,
                 // 303-315); partial dots are exchanged between the column parts
                 const float s = row_sum<NPARTS>(x, 2, ps) + bs, t = row_sum<NPARTS>(x, 3, pt_) + bt;
@@ -605,20 +646,11 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
                     tmem_st1(x.tb + dst_lo, *reinterpret_cast<const uint32_t*>(&lo2));
                 }
                 // end of the block: its two last-layer chunks go back; next block (or the q density) starts
-                if (arrive_last<NCW>(x, &bars->cnt_fin)) {
-                    release(x, x.rel_it);
-                    release(x, x.rel_it + 1);
-                    if (more) {
-                        job<NPASS>(x, x.issue_it, 0, kT2UHi, kT2ULo, Ku, Hc);
-                        job<NPASS>(x, x.issue_it + 1, 1, kT2UHi, kT2ULo, Ku, Hc);
-                    } else {
-                        job<NPASS>(x, x.issue_it, 0, kT2InHi, kT2InLo, Kin, Wd);
-                        job<NPASS>(x, x.issue_it + 1, 1, kT2InHi, kT2InLo, Kin, Wd);
-                    }
-                }
-                x.rel_it += 2; x.issue_it += 2;
+                warp_arrive(x, &bars->fin);
+                T2_TICK(11)  // coupling update + handoff
             }
         }
+        T2_TICK(10)  // tail
         if (valid && x.part == 0) {
             const float lp = normal_lp2(z0, z1, prev0, prev1, ts.std[0], ts.std[1]) + lacc;
             a.out[ag * a.out_sa + rem * a.out_sp + (long long)step * a.out_st] = lp;
@@ -638,14 +670,14 @@ inline int tc2_launch_separate(const T2Dims& dm, const T2Step* d_steps, const un
                "2*(cond_size + 2*pred_len) <= 96); use FC_PREC_FP32";
         return 1;
     }
-    const size_t smem = 9728 + (size_t)dm.nslots * dm.slot_bytes;
+    const size_t smem = 10240 + (size_t)dm.nslots * dm.slot_bytes;
     if ((int)smem > smem_optin) { *msg = "tensor-core path: shared-memory budget exceeded"; return 1; }
     cudaError_t e = cudaFuncSetAttribute(k_separate_tc2<NPASS, NPARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { *msg = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return 1; }
     const long long tiles = (a.N + 127) / 128;
     const long long items = tiles * dm.T;
     const int grid = (int)(items < num_sms ? items : num_sms);
-    k_separate_tc2<NPASS, NPARTS><<<grid, NPARTS * 128 + 32, smem, stream>>>(d_steps, d_img, a, dm, tiles, items);
+    k_separate_tc2<NPASS, NPARTS><<<grid, NPARTS * 128 + 64, smem, stream>>>(d_steps, d_img, a, dm, tiles, items);
     (*launches)++;
     e = cudaGetLastError();
     if (e != cudaSuccess) { *msg = std::string("k_separate_tc2 launch: ") + cudaGetErrorString(e); return 1; }
