@@ -39,6 +39,8 @@ struct fc_handle {
     unsigned char* d_t2img[2] = {nullptr, nullptr};
     fc::T2Step* d_t2steps[2] = {nullptr, nullptr};
     fc::T2Dims t2dims[2]{};
+    float* d_upd = nullptr;           // rapid update: per-(agent, chunk) partial sums
+    size_t upd_floats = 0;
     float* d_scratch = nullptr;       // K>1 importance-sample staging
     size_t scratch_floats = 0;
     Dims dims{};
@@ -121,6 +123,7 @@ extern "C" void fc_destroy(fc_handle* h) {
     cudaFree(h->d_tcsteps);
     for (int i = 0; i < 2; ++i) { cudaFree(h->d_t2img[i]); cudaFree(h->d_t2steps[i]); }
     cudaFree(h->d_scratch);
+    cudaFree(h->d_upd);
     delete h;
 }
 
@@ -485,9 +488,22 @@ extern "C" int fc_update(fc_handle* h, const float* new_pos, int t, const float*
     if (A < 0 || S < 0) return fail(h, "negative size");
     if (A == 0 || S == 0) return 0;
     if (!new_pos || !prob_st_0 || !ldjs || !normalizer || !prob_st_t) return fail(h, "null tensor pointer");
-    k_update<<<(unsigned)A, 512, 0, (cudaStream_t)stream>>>(new_pos, t, T, prob_st_0, ldjs, normalizer, prob_st_t, S,
-                                                            h->plans[t].std[0], h->plans[t].std[1]);
-    h->launches++;
+    const int nchunk = (int)((S + kUpdChunk - 1) / kUpdChunk);
+    const size_t need = (size_t)A * nchunk;
+    if (need > h->upd_floats) {            // partial sums live in a handle-owned buffer (grown outside graph capture)
+        FC_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+        FC_CUDA(h, cudaFree(h->d_upd));
+        h->d_upd = nullptr; h->upd_floats = 0;
+        FC_CUDA(h, cudaMalloc(&h->d_upd, need * sizeof(float)));
+        h->upd_floats = need;
+    }
+    if (A > 65535) return fail(h, "too many agents for one update launch (%lld)", (long long)A);
+    dim3 grid((unsigned)nchunk, (unsigned)A);
+    k_update_partial<<<grid, kUpdChunk, 0, (cudaStream_t)stream>>>(new_pos, t, T, prob_st_0, h->d_upd, S, nchunk, h->plans[t].std[0],
+                                                                  h->plans[t].std[1]);
+    k_update_write<<<grid, kUpdChunk, 0, (cudaStream_t)stream>>>(new_pos, t, T, prob_st_0, ldjs, normalizer, h->d_upd, prob_st_t, S, nchunk,
+                                                                h->plans[t].std[0], h->plans[t].std[1]);
+    h->launches += 2;
     FC_CUDA(h, cudaGetLastError());
     return 0;
 }

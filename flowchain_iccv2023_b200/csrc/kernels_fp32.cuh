@@ -546,35 +546,61 @@ __global__ void k_base_normalizer(const float* __restrict__ base_lp, float* __re
     if (threadIdx.x == 0) norm[blockIdx.x] = acc;
 }
 
-__global__ void __launch_bounds__(512)
-k_update(const float* __restrict__ new_pos, int t, int T, const float* __restrict__ prob0,
-         const float* __restrict__ ldjs, const float* __restrict__ normalizer, float* __restrict__ out,
-         long long S, float sd0, float sd1) {
+// Rapid update, two streaming passes over an (agents x sample-chunks) grid so that ONE agent (the reference's only
+// working case, B = 1) already spreads over ~40 SMs:
+//   pass 1: partial[a][c] = sum over the chunk's samples of exp(base log-prob at the newest observed position)
+//   pass 2: total = sum_c partial[a][c] (fixed order -> deterministic), per-sample log(bp / total * normalizer) into
+//           shared memory, then a flat, coalesced copy of prob_st_0[:, :, t:] with the log-prob column replaced by
+//           lp'[s] + ldjs[s, t+j].
+constexpr int kUpdChunk = 256;      // samples per CTA
+
+__global__ void __launch_bounds__(kUpdChunk)
+k_update_partial(const float* __restrict__ new_pos, int t, int T, const float* __restrict__ prob0, float* __restrict__ partial,
+                 long long S, int nchunk, float sd0, float sd1) {
     __shared__ float red[32];
-    const long long ag = blockIdx.x;
-    const float l0 = __ldg(new_pos + ag * 2), l1 = __ldg(new_pos + ag * 2 + 1);
-    const float* p0 = prob0 + ag * S * T * 3;
-    float acc = 0.0f;
-    for (long long s = threadIdx.x; s < S; s += blockDim.x) {
-        const float* q = p0 + (s * T + (t - 1)) * 3;
-        acc += expf(normal_lp2(__ldg(q), __ldg(q + 1), l0, l1, sd0, sd1));
+    const long long ag = blockIdx.y;
+    const long long s = (long long)blockIdx.x * kUpdChunk + threadIdx.x;
+    float v = 0.0f;
+    if (s < S) {
+        const float* q = prob0 + ((ag * S + s) * T + (t - 1)) * 3;
+        v = expf(normal_lp2(__ldg(q), __ldg(q + 1), __ldg(new_pos + ag * 2), __ldg(new_pos + ag * 2 + 1), sd0, sd1));
     }
-    const float total = block_sum(acc, red);
+    v = block_sum(v, red);
+    if (threadIdx.x == 0) partial[ag * nchunk + blockIdx.x] = v;
+}
+
+__global__ void __launch_bounds__(kUpdChunk)
+k_update_write(const float* __restrict__ new_pos, int t, int T, const float* __restrict__ prob0, const float* __restrict__ ldjs,
+               const float* __restrict__ normalizer, const float* __restrict__ partial, float* __restrict__ out, long long S,
+               int nchunk, float sd0, float sd1) {
+    __shared__ float lp_new[kUpdChunk];
+    const long long ag = blockIdx.y;
+    const long long s0 = (long long)blockIdx.x * kUpdChunk;
+    float total = 0.0f;
+    for (int c = 0; c < nchunk; ++c) total += __ldg(partial + ag * nchunk + c);
     const float nz = __ldg(normalizer + ag);
-    const int Tt = T - t;
-    const float* lj = ldjs + ag * S * T;
-    float* o = out + ag * S * Tt * 3;
-    for (long long s = threadIdx.x; s < S; s += blockDim.x) {
-        const float* q = p0 + (s * T + (t - 1)) * 3;
-        const float bp = expf(normal_lp2(__ldg(q), __ldg(q + 1), l0, l1, sd0, sd1));
-        const float lp = logf(bp / total * nz);
-        for (int j = 0; j < Tt; ++j) {
-            const float* src = p0 + (s * T + t + j) * 3;
-            float* dst = o + (s * Tt + j) * 3;
-            dst[0] = __ldg(src);
-            dst[1] = __ldg(src + 1);
-            dst[2] = lp + __ldg(lj + s * T + t + j);
+    {
+        const long long s = s0 + threadIdx.x;
+        float lp = 0.0f;
+        if (s < S) {
+            const float* q = prob0 + ((ag * S + s) * T + (t - 1)) * 3;
+            const float bp = expf(normal_lp2(__ldg(q), __ldg(q + 1), __ldg(new_pos + ag * 2), __ldg(new_pos + ag * 2 + 1), sd0, sd1));
+            lp = logf(bp / total * nz);       // same order of operations as fastpredNF.py:154-155
         }
+        lp_new[threadIdx.x] = lp;
+    }
+    __syncthreads();
+    const int Tt = T - t, per = Tt * 3;
+    const long long ns = (S - s0) < kUpdChunk ? (S - s0) : kUpdChunk;
+    const float* src = prob0 + (ag * S + s0) * T * 3;
+    const float* lj = ldjs + (ag * S + s0) * T;
+    float* dst = out + (ag * S + s0) * per;
+    for (long long e = threadIdx.x; e < ns * per; e += kUpdChunk) {
+        const int sl = (int)(e / per), r = (int)(e - (long long)sl * per), j = r / 3, c = r - j * 3;
+        float v;
+        if (c < 2) v = __ldg(src + ((long long)sl * T + t + j) * 3 + c);
+        else v = lp_new[sl] + __ldg(lj + (long long)sl * T + t + j);
+        dst[e] = v;
     }
 }
 
