@@ -34,6 +34,30 @@ METRIC = "log_density_evals_per_sec"
 UNIT = "evals/s"
 
 
+def ncu_traffic(precision: str):
+    """DRAM bytes (read + write) of ONE launch of the dominant kernel, from the committed `ncu --set full` capture of
+    this same command (profiles/): None when no capture exists for the chosen precision."""
+    name = {"f16x3": "r01_ncu_full_k_separate_tc2_f16x3.csv", "fp32": None}.get(precision)
+    path = os.path.join(ROOT, "profiles", name) if name else None
+    if not path or not os.path.exists(path):
+        return None
+    import csv
+    rows = list(csv.reader(open(path)))
+    if len(rows) < 3:
+        return None
+    hdr, unit, val = rows[0], rows[1], rows[2]
+    tot = 0.0
+    for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        if key not in hdr:
+            return None
+        i = hdr.index(key)
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit[i], None)
+        if scale is None:
+            return None
+        tot += float(val[i]) * scale
+    return tot
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -287,7 +311,9 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
+                         "traffic": ncu_traffic(args.precision) if (A == 64 and n == 256) else None,
+                         "traffic_note": "dram read+write bytes of one launch, ncu --set full capture in profiles/ (algorithmic output: %d B)" % (A * G * T * 4),
+                         "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
                          "kernel_ms": kern_ms, "algorithmic_flops_per_launch": flops_launch},
         }
         if world == 1 and not args.no_cpu_baseline:
