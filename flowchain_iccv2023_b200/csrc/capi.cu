@@ -524,3 +524,12 @@ extern "C" int fc_debug_t2prof(unsigned long long* out16, int reset) {
     }
     return 0;
 }
+
+extern "C" int fc_debug_t2trace(unsigned long long* out, int reset) {   // 12 x 256 entries, (tag << 48) | clock
+    if (out && cudaMemcpyFromSymbol(out, fc::g_t2trace, sizeof(unsigned long long) * 12 * 256) != cudaSuccess) return 1;
+    if (reset) {
+        static unsigned long long z[12 * 256];
+        if (cudaMemcpyToSymbol(fc::g_t2trace, z, sizeof z) != cudaSuccess) return 1;
+    }
+    return 0;
+}

@@ -25,6 +25,7 @@
 namespace fc {
 
 constexpr int kT2MaxChunks = 12 + 2 * (kMaxHidden + 1) * kMaxBlocks;
+constexpr uint32_t kT2Slots = 8;       // weight-ring depth (power of two: ring arithmetic is a mask/shift)
 // tensor-memory column map (32-bit columns, 128 lanes = rows)
 constexpr uint32_t kT2Acc0 = 0, kT2Acc1 = 96;            // fp32 accumulators of net 0 / net 1 (N <= 96)
 constexpr uint32_t kT2InHi = 192, kT2InLo = 216;         // [z|w, cond, prefix] operand, K <= 48
@@ -134,14 +135,14 @@ inline void tc2_pack(const fc_model_desc& d, const std::vector<StepPlan>& plans,
             auto density = [&](bool first) {
                 // L1 of both nets reads the input operand; `fin` was awaited by the caller's first entry
                 put(3, 0, 0, ts.Kin, ts.Wd, 0);
-                put(0, 1, 0, ts.Kin, ts.Wd, first ? 0 : 2);          // q: hand back the last block's last-layer chunks
+                put(3, 1, 0, ts.Kin, ts.Wd, 0);
                 for (int l = 0; l < 2; ++l)
                     for (int net = 0; net < 2; ++net) put(1 + net, net, 2, ts.Wd, l == 0 ? ts.Wd : ts.CPd, 1);
             };
             density(true);
             for (int b = 0; b < sp.n_blocks; ++b) {
                 put(3, 0, 1, ts.Ku, H, 0);
-                put(0, 1, 1, ts.Ku, H, 2);                            // L3 chunks of r / last-layer chunks of block b-1
+                put(3, 1, 1, ts.Ku, H, 0);
                 for (int l = 0; l < sp.n_hidden; ++l)
                     for (int net = 0; net < 2; ++net) put(1 + net, net, 2, H, H, 1);
             }
@@ -151,9 +152,8 @@ inline void tc2_pack(const fc_model_desc& d, const std::vector<StepPlan>& plans,
     }
     while (img.size() % 128) img.push_back(0);
     dm.slot_bytes = (dm.slot_bytes + 127) / 128 * 128;
-    dm.nslots = (smem_optin - 10240) / dm.slot_bytes;
-    if (dm.nslots > 12) dm.nslots = 12;
-    dm.supported = dm.nslots >= 3;
+    dm.nslots = (int32_t)kT2Slots;
+    dm.supported = 10240 + (size_t)kT2Slots * dm.slot_bytes <= (size_t)smem_optin;
 }
 
 #ifndef FC_T2_PROF
@@ -166,6 +166,18 @@ __device__ unsigned long long g_t2prof[16];
         asm volatile("mov.u64 %0, %%clock64;" : "=l"(now_));                            \
         atomicAdd(&g_t2prof[i], (unsigned long long)(now_ - prof_t));                   \
         prof_t = now_;                                                                  \
+    }
+
+#ifndef FC_T2_TRACE
+#define FC_T2_TRACE 0
+#endif
+// development aid: event timeline of one item (CTA 0) -- g_trace[warp][k] = (tag << 48) | clock
+__device__ unsigned long long g_t2trace[12][256];
+#define T2_EV(tag)                                                                                   \
+    if (FC_T2_TRACE && blockIdx.x == 0 && trace_on && (threadIdx.x & 31) == 0 && trace_n < 256) {    \
+        long long now_;                                                                              \
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(now_));                                         \
+        g_t2trace[threadIdx.x >> 5][trace_n++] = ((unsigned long long)(tag) << 48) | ((unsigned long long)now_ & 0xFFFFFFFFFFFFull); \
     }
 
 namespace t2 {
@@ -183,23 +195,45 @@ __device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t r) {
 
 __device__ __forceinline__ float clamp_h(float v) { return fminf(fmaxf(v, -65000.0f), 65000.0f); }
 
-// 8 fp32 values -> 4 packed fp16 pairs (hi) and the 4 packed residual pairs (lo)
-template <int NPASS>
+// 8 fp32 values -> 4 packed fp16 pairs (hi) and the 4 packed residual pairs (lo), with an optional fused ReLU.
+// NPASS = 3: hi is the value TRUNCATED to fp16's 11 significant bits (one LOP3 on the integer pipe; exactly
+// representable, so the pack is exact), lo = a - hi in fp32 (same sign as a), both packed with
+// F2FP[.RELU][.SATFINITE] -- ReLU and the fp16 overflow clamp ride on the pack instruction for free.
+// NPASS = 1: hi is the value rounded to fp16.
+template <int NPASS, bool RELU>
 __device__ __forceinline__ void split8(const float* a, uint32_t* hi, uint32_t* lo) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const __half2 h = __floats2half2_rn(a[2 * i], a[2 * i + 1]);
-        hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+        const float a0 = a[2 * i], a1 = a[2 * i + 1];
         if (NPASS == 3) {
-            const float2 f = __half22float2(h);
-            const __half2 l = __floats2half2_rn(a[2 * i] - f.x, a[2 * i + 1] - f.y);
-            lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+            const float h0 = __uint_as_float(__float_as_uint(a0) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(a1) & 0xFFFFE000u);
+            const float l0 = a0 - h0, l1 = a1 - h1;
+            if (RELU) {
+                asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi[i]) : "f"(h1), "f"(h0));
+                asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo[i]) : "f"(l1), "f"(l0));
+            } else {
+                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi[i]) : "f"(h1), "f"(h0));
+                asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo[i]) : "f"(l1), "f"(l0));
+            }
+        } else {
+            if (RELU) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi[i]) : "f"(a1), "f"(a0));
+            else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi[i]) : "f"(a1), "f"(a0));
         }
     }
 }
-// tanh(x) = 1 - 2 / (1 + e^{2x}), |err| ~ 5e-7 (MUFU.TANH itself is only 2^-11 accurate).  Two MUFU ops (ex2, rcp) and
-// four FMA-pipe ops per value; an FMA-pipe Newton reciprocal was measured slower (the FP32 pipe, not MUFU, is the
-// scarcer resource in these epilogues).
+// tanh(x) = 1 - 2 / (1 + e^{2x}), |err| ~ 5e-7 (MUFU.TANH itself is only 2^-11 accurate).  Two values share ONE
+// reciprocal (r = 1/(y0 y1), 1/y0 = r y1, 1/y1 = r y0): 1.5 MUFU ops per value instead of 2.
+__device__ __forceinline__ void tanh_acc2(float& x0, float& x1) {
+    float e0, e1;
+    const float c = 2.885390081777927f;                        // 2 log2(e)
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(x0, 15.0f) * c));   // clamp: keeps y0*y1 finite, tanh(15) == 1
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(x1, 15.0f) * c));
+    const float y0 = e0 + 1.0f, y1 = e1 + 1.0f;
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y0 * y1));
+    x0 = fmaf(-2.0f * y1, r, 1.0f);
+    x1 = fmaf(-2.0f * y0, r, 1.0f);
+}
 __device__ __forceinline__ float tanh_acc(float x) {
     float e;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
@@ -227,8 +261,8 @@ struct X {
     float* part_buf;            // [4][NPARTS][128] row-partial exchange
 };
 
-__device__ __forceinline__ const uint8_t* slot_ptr(const X& x, uint32_t it) { return x.slots + (size_t)(it % x.nslots) * x.slot_bytes; }
-__device__ __forceinline__ void wait_full(const X& x, uint32_t it) { mbar_wait(&x.bars->full[it % x.nslots], (it / x.nslots) & 1u); }
+__device__ __forceinline__ const uint8_t* slot_ptr(const X& x, uint32_t it) { return x.slots + (size_t)(it % kT2Slots) * x.slot_bytes; }
+__device__ __forceinline__ void wait_full(const X& x, uint32_t it) { mbar_wait(&x.bars->full[it % kT2Slots], (it / kT2Slots) & 1u); }
 __device__ __forceinline__ void wait_mma(X& x, int net) {
     if (net == 0) { mbar_wait(&x.bars->mma_done[0], x.mma_cnt0 & 1u); x.mma_cnt0++; }
     else { mbar_wait(&x.bars->mma_done[1], x.mma_cnt1 & 1u); x.mma_cnt1++; }
@@ -265,11 +299,15 @@ template <int NPASS, int ACT, bool DOT, bool WRITE>
 __device__ __forceinline__ void epi_chunk(float* u, int c0, uint32_t bias, uint32_t wlast, uint32_t ohi, uint32_t olo, float& dot) {
     const float4 b0 = lds128(bias + (uint32_t)c0 * 4), b1 = lds128(bias + (uint32_t)c0 * 4 + 16);
     u[0] += b0.x; u[1] += b0.y; u[2] += b0.z; u[3] += b0.w; u[4] += b1.x; u[5] += b1.y; u[6] += b1.z; u[7] += b1.w;
+    if (ACT == ACT_T) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        if (ACT == ACT_R) u[q] = fminf(fmaxf(u[q], 0.0f), 65000.0f);
-        else if (NPASS == 3) u[q] = tanh_acc(u[q]);
-        else asm("tanh.approx.f32 %0, %0;" : "+f"(u[q]));
+        for (int q = 0; q < 8; q += 2) {
+            if (NPASS == 3) tanh_acc2(u[q], u[q + 1]);
+            else { asm("tanh.approx.f32 %0, %0;" : "+f"(u[q])); asm("tanh.approx.f32 %0, %0;" : "+f"(u[q + 1])); }
+        }
+    } else if (DOT) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) u[q] = fmaxf(u[q], 0.0f);      // (with WRITE the ReLU is fused into the fp16 pack)
     }
     if (DOT) {
         const float4 w0 = lds128(wlast + (uint32_t)c0 * 4), w1 = lds128(wlast + (uint32_t)c0 * 4 + 16);
@@ -278,7 +316,7 @@ __device__ __forceinline__ void epi_chunk(float* u, int c0, uint32_t bias, uint3
     }
     if (WRITE) {
         uint32_t hi[4], lo[4];
-        split8<NPASS>(u, hi, lo);
+        split8<NPASS, ACT == ACT_R>(u, hi, lo);
         tmem_st4(ohi + (uint32_t)(c0 >> 1), hi);
         if (NPASS == 3) tmem_st4(olo + (uint32_t)(c0 >> 1), lo);
     }
@@ -332,30 +370,37 @@ __device__ __noinline__ void mma_issue(Bars* bars, const uint8_t* chunk, uint32_
     const uint32_t acc = tb0 + (net ? kT2Acc1 : kT2Acc0);
     const uint64_t dhi = umma_desc(b_hi, 128, sbo), dlo = umma_desc(b_lo, 128, sbo);
     const int nk = (FC_T2_ABLATE & 2) ? 0 : (Kp >> 4);
-#pragma unroll 1
-    for (int ks = 0; ks < nk; ++ks) umma_ts_elect(acc, tb0 + a_hi + ks * 8, dhi + (uint64_t)(ks * 16), idesc, ks > 0 ? 1u : 0u);
-    if (NPASS == 3) {
-#pragma unroll 1
-        for (int ks = 0; ks < nk; ++ks) umma_ts_elect(acc, tb0 + a_lo + ks * 8, dhi + (uint64_t)(ks * 16), idesc, 1u);
-#pragma unroll 1
-        for (int ks = 0; ks < nk; ++ks) umma_ts_elect(acc, tb0 + a_hi + ks * 8, dlo + (uint64_t)(ks * 16), idesc, 1u);
+    // The per-MMA operand set-up (address adds + moves into uniform registers) has ~100 cycles of dependent latency;
+    // unrolled by 6 (= the largest K/16) the set-ups of one pass overlap and the loop is paced by the tensor pipe.
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(leader));
+    if (leader) {
+#pragma unroll 6
+        for (int ks = 0; ks < nk; ++ks) umma_ts(acc, tb0 + a_hi + ks * 8, dhi + (uint64_t)(ks * 16), idesc, ks > 0 ? 1u : 0u);
+        if (NPASS == 3) {
+#pragma unroll 6
+            for (int ks = 0; ks < nk; ++ks) umma_ts(acc, tb0 + a_lo + ks * 8, dhi + (uint64_t)(ks * 16), idesc, 1u);
+#pragma unroll 6
+            for (int ks = 0; ks < nk; ++ks) umma_ts(acc, tb0 + a_hi + ks * 8, dlo + (uint64_t)(ks * 16), idesc, 1u);
+        }
+        umma_commit(&bars->mma_done[net]);
     }
-    umma_commit_elect(&bars->mma_done[net]);
+    __syncwarp();
 }
 
 }  // namespace t2
 
 // Warp roles: [0, 4*NPARTS) compute (warp w: lane quadrant w % 4, column part w / 4), then the weight producer (TMA)
-// and the MMA issuer.  No CTA-wide barrier inside an item: roles hand work to each other through mbarriers only
+// and two MMA issuers (one per net).  No CTA-wide barrier inside an item: roles hand work to each other through mbarriers only
 // (epilogue(l) -> `opnd` -> MMA(l+1) -> tcgen05.commit -> `mma_done` -> epilogue(l+1)).
 template <int NPASS, int NPARTS>
-__global__ void __launch_bounds__(NPARTS * 128 + 64, 1)
+__global__ void __launch_bounds__(NPARTS * 128 + 96, 1)
 k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img, RowArgs a, T2Dims dm, long long tiles_per_step,
                long long total_items) {
     using namespace tc;
     using namespace t2;
     constexpr int NCW = 4 * NPARTS;                  // compute warps
-    constexpr int kThreadsAll = NPARTS * 128 + 64;
+    constexpr int kThreadsAll = NPARTS * 128 + 96;
     extern __shared__ __align__(128) uint8_t smem_t2[];
     uint8_t* smem = smem_t2;
     Bars* bars = reinterpret_cast<Bars*>(smem);
@@ -368,7 +413,7 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < dm.nslots; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+        for (int s = 0; s < (int)kT2Slots; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
         mbar_init(&bars->mma_done[0], 1);
         mbar_init(&bars->mma_done[1], 1);
         mbar_init(&bars->opnd[0], NCW);
@@ -393,9 +438,13 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
 
     long long prof_t = 0;
     if (FC_T2_PROF) asm volatile("mov.u64 %0, %%clock64;" : "=l"(prof_t));
+    int trace_n = 0, item_no = 0;
+    bool trace_on = false;
     for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
         const int step = dm.T - 1 - (int)(item / tiles_per_step);      // heavy (late) steps first
         const long long tile = item % tiles_per_step;
+        trace_on = (item_no++ == 5);
+        T2_EV(1)
         T2_TICK(0)   // tail of previous item (output store)
         __syncthreads();
         {
@@ -412,8 +461,8 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
             // ===== weight producer: stream the step's chunks through the ring =====
             for (int ci = 0; ci < ts.nchunks; ++ci, ++ring_it) {
                 if (lane == 0) {
-                    const uint32_t slot = ring_it % dm.nslots;
-                    mbar_wait(&bars->empty[slot], ((ring_it / dm.nslots) & 1u) ^ 1u);
+                    const uint32_t slot = ring_it % kT2Slots;
+                    mbar_wait(&bars->empty[slot], ((ring_it / kT2Slots) & 1u) ^ 1u);
                     if (FC_T2_ABLATE & 4) mbar_arrive(&bars->full[slot]);
                     else {
                     mbar_expect_tx(&bars->full[slot], (uint32_t)ts.chunk_bytes[ci]);
@@ -425,28 +474,57 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
             continue;
         }
 
-        if (warp == NCW + 1) {
-            // ===== MMA issuer (whole warp convergent, one elected lane issues): runs the step's job table.  A stage's
-            // weight chunk is handed back AFTER the dependent MMAs are issued: the release is off the critical path. =====
-            uint32_t rel = ring_it;
+        if (warp > NCW) {
+            // ===== MMA issuers, one warp per net (whole warp convergent, one elected lane issues).  Issuing a
+            // net-layer costs ~1-2k cycles of this warp's time (operand set-up through uniform registers), so one
+            // issuer for both nets was the critical path; with one per net the two chains are independent.
+            // Net n owns chunks n, n+2, ... of the step; after issuing job j it hands back the chunk of job j-1,
+            // whose epilogue finished before the barrier this job waited on. =====
+            const int net = warp - NCW - 1;
+            uint64_t* opnd_bar = &bars->opnd[net];
+            uint64_t* done_bar = &bars->mma_done[net];
+            const uint32_t base = ring_it;
+            const uint32_t acc = x.tb0 + (net ? kT2Acc1 : kT2Acc0);
+            int prev = -1;
 #pragma unroll 1
-            for (int ci = 0; ci < ts.nchunks; ++ci, ++ring_it) {
-                const int w = ts.job_wait[ci], net = ts.job_net[ci], src = ts.job_src[ci];
-                if (w == 1) { mbar_wait(&bars->opnd[0], opnd_cnt0 & 1u); opnd_cnt0++; }
-                else if (w == 2) { mbar_wait(&bars->opnd[1], opnd_cnt1 & 1u); opnd_cnt1++; }
-                else if (w == 3) { mbar_wait(&bars->fin, fin_cnt & 1u); fin_cnt++; }
-                mbar_wait(&bars->full[ring_it % dm.nslots], (ring_it / dm.nslots) & 1u);
+            for (int ci = net; ci < ts.nchunks; ci += 2) {
+                // ---- everything that does not depend on the operand being ready: weights present, descriptors ----
+                const uint32_t it = base + (uint32_t)ci;
+                mbar_wait(&bars->full[it % kT2Slots], (it / kT2Slots) & 1u);
+                const int w = ts.job_wait[ci], src = ts.job_src[ci], Kp = ts.job_kp[ci], N = ts.job_n[ci];
+                const uint32_t a_hi = x.tb0 + (src == 0 ? kT2InHi : (src == 1 ? kT2UHi : (net ? kT2H1Hi : kT2H0Hi)));
+                const uint32_t a_lo = x.tb0 + (src == 0 ? kT2InLo : (src == 1 ? kT2ULo : (net ? kT2H1Lo : kT2H0Lo)));
+                const uint32_t b_hi = smem_u32(slots + (size_t)(it % kT2Slots) * dm.slot_bytes);
+                const uint32_t idesc = umma_idesc_f16(128, N), sbo = (uint32_t)(Kp >> 3) * 128u;
+                const uint64_t dhi = umma_desc(b_hi, 128, sbo), dlo = umma_desc(b_hi + (uint32_t)(N * Kp * 2), 128, sbo);
+                const int nk = (FC_T2_ABLATE & 2) ? 0 : (Kp >> 4);
+                uint32_t leader;
+                asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(leader));
+                // ---- critical path: operand ready -> MMAs -> commit ----
+                if (w == 3) { mbar_wait(&bars->fin, fin_cnt & 1u); fin_cnt++; }
+                else { mbar_wait(opnd_bar, opnd_cnt0 & 1u); opnd_cnt0++; }
                 tc_fence_after();
-                const uint32_t a_hi = src == 0 ? kT2InHi : (src == 1 ? kT2UHi : (net ? kT2H1Hi : kT2H0Hi));
-                const uint32_t a_lo = src == 0 ? kT2InLo : (src == 1 ? kT2ULo : (net ? kT2H1Lo : kT2H0Lo));
-                mma_issue<NPASS>(bars, slots + (size_t)(ring_it % dm.nslots) * dm.slot_bytes, x.tb0, net, a_hi, a_lo, ts.job_kp[ci], ts.job_n[ci]);
-#pragma unroll 1
-                for (int r = 0; r < ts.job_rel[ci]; ++r, ++rel) mbar_arrive_elect(&bars->empty[rel % dm.nslots]);
+                T2_EV(300 + ci)
+                if (leader) {
+#pragma unroll 6
+                    for (int ks = 0; ks < nk; ++ks) umma_ts(acc, a_hi + ks * 8, dhi + (uint64_t)(ks * 16), idesc, ks > 0 ? 1u : 0u);
+                    if (NPASS == 3) {
+#pragma unroll 6
+                        for (int ks = 0; ks < nk; ++ks) umma_ts(acc, a_lo + ks * 8, dhi + (uint64_t)(ks * 16), idesc, 1u);
+#pragma unroll 6
+                        for (int ks = 0; ks < nk; ++ks) umma_ts(acc, a_hi + ks * 8, dlo + (uint64_t)(ks * 16), idesc, 1u);
+                    }
+                    umma_commit(done_bar);
+                }
+                __syncwarp();
+                T2_EV(400 + ci)
+                if (prev >= 0) mbar_arrive_elect(&bars->empty[(base + (uint32_t)prev) % kT2Slots]);
+                prev = ci;
             }
             mbar_wait(&bars->fin, fin_cnt & 1u);                     // final q-density epilogue done
             fin_cnt++;
-#pragma unroll 1
-            for (int r = 0; r < ts.tail_rel; ++r, ++rel) mbar_arrive_elect(&bars->empty[rel % dm.nslots]);
+            mbar_arrive_elect(&bars->empty[(base + (uint32_t)prev) % kT2Slots]);
+            ring_it += (uint32_t)ts.nchunks;
             continue;
         }
 
@@ -478,7 +556,7 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
                     v[i] = clamp_h(val);
                 }
                 uint32_t hi[4], lo[4];
-                split8<NPASS>(v, hi, lo);
+                split8<NPASS, false>(v, hi, lo);
                 tmem_st4(x.tb + kT2InHi + (uint32_t)(k0 >> 1), hi);
                 if (NPASS == 3) tmem_st4(x.tb + kT2InLo + (uint32_t)(k0 >> 1), lo);
             }
@@ -486,6 +564,7 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
         T2_TICK(2)   // row setup + input gather
         // first sub-network: both r-density nets read the input operand
         warp_arrive(x, &bars->fin);
+        T2_EV(2)
 
 #pragma unroll 1
         for (int which = 0; which < 2; ++which) {
@@ -496,7 +575,9 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
                 for (int net = 0; net < 2; ++net) {
                     const uint32_t bias = smem_u32(slot_ptr(x, x.chunk_it)) + (uint32_t)((NPASS == 3 ? 2 : 1) * Wd * (l == 0 ? Kin : Wd) * 2);
                     wait_mma(x, net);        // (the issuing warp acquired the weight chunk; the commit orders it for us)
+                    T2_EV(10 + which * 100 + l * 2 + net)
                     epi_hidden<NPASS, NPARTS, ACT_R, false, true>(x, net, Wd, bias, 0u);
+                    T2_EV(20 + which * 100 + l * 2 + net)
                     warp_arrive(x, &bars->opnd[net]);
                     x.chunk_it++;
                 }
@@ -509,6 +590,7 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
             x.chunk_it += 2;
             wait_mma(x, 0);
             wait_mma(x, 1);
+            T2_EV(30 + which * 100)
             T2_TICK(4 + which * 4)   // wait for L3 MMAs (4: r, 8: q)
             if (which == 0) {
                 // sample u = exp(ls) eps + mu (fastpredNF.py:727-733) -> [u, mx] operand; log r = -C/2 log 2pi - sum ls - 1/2 sum eps^2
@@ -550,7 +632,7 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
                             if (i == (C & 7)) { u[i] = m0 == 0 ? clamp_h(z0) : 0.0f; u[i + 1] = m0 == 1 ? clamp_h(z1) : 0.0f; }
                     }
                     uint32_t hi[4], lo[4];
-                    split8<3>(u, hi, lo);     // u is always kept as a hi+lo pair: log q needs it back at full precision
+                    split8<3, false>(u, hi, lo);     // u is always kept as a hi+lo pair: log q needs it back at full precision
                     tmem_st4(x.tb + kT2UHi + (uint32_t)(d0 >> 1), hi);
                     tmem_st4(x.tb + kT2ULo + (uint32_t)(d0 >> 1), lo);
                 }
@@ -586,6 +668,7 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
             T2_TICK(5 + which * 4)   // final density epilogue E2 / E3 (5: r, 9: q)
             // end of the density sub-network: its two L3 chunks go back; after r the first coupling starts
             warp_arrive(x, &bars->fin);
+            T2_EV(40 + which * 100)
             if (which == 1) break;
 
             // ============ n_blocks x (masked affine coupling + BatchNorm), forward ============
@@ -602,11 +685,13 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
                         x.chunk_it++;
                         T2_TICK(6)
                         wait_mma(x, net);
+                        T2_EV(50 + b * 10 + l * 2 + net)
                         T2_TICK(12 + net)   // wait for the MMA of (l, net)
                         if (!last) {
                             if (net == 0) epi_hidden<NPASS, NPARTS, ACT_T, false, true>(x, 0, Hc, tail, 0u);
                             else epi_hidden<NPASS, NPARTS, ACT_R, false, true>(x, 1, Hc, tail, 0u);
                             T2_TICK(14)     // epilogue math
+                            T2_EV(60 + b * 10 + l * 2 + net)
                             warp_arrive(x, &bars->opnd[net]);
                             T2_TICK(15)     // arrive
                         } else {
@@ -615,6 +700,7 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
                         }
                     }
                 }
+                T2_EV(80 + b)
                 T2_TICK(6)   // coupling layers (all blocks)
                 // both nets done: affine update of the unmasked coordinate + BatchNorm (TFCondARFlow.py:360-381,
                 // 303-315); partial dots are exchanged between the column parts
@@ -647,6 +733,7 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
                 }
                 // end of the block: its two last-layer chunks go back; next block (or the q density) starts
                 warp_arrive(x, &bars->fin);
+                T2_EV(90 + b)
                 T2_TICK(11)  // coupling update + handoff
             }
         }
@@ -677,7 +764,7 @@ inline int tc2_launch_separate(const T2Dims& dm, const T2Step* d_steps, const un
     const long long tiles = (a.N + 127) / 128;
     const long long items = tiles * dm.T;
     const int grid = (int)(items < num_sms ? items : num_sms);
-    k_separate_tc2<NPASS, NPARTS><<<grid, NPARTS * 128 + 64, smem, stream>>>(d_steps, d_img, a, dm, tiles, items);
+    k_separate_tc2<NPASS, NPARTS><<<grid, NPARTS * 128 + 96, smem, stream>>>(d_steps, d_img, a, dm, tiles, items);
     (*launches)++;
     e = cudaGetLastError();
     if (e != cudaSuccess) { *msg = std::string("k_separate_tc2 launch: ") + cudaGetErrorString(e); return 1; }
