@@ -49,17 +49,20 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
     return ctr;
 }
 
+// Box-Muller on fast intrinsics: the noise only has to be N(0,1) to ~1e-6 (it is a Monte-Carlo draw, and both
+// precision paths must see the SAME values, which they do because this one function serves all kernels).
+// The angle is kept in [-pi, pi) where __sincosf is accurate to ~2^-21.
 __device__ __noinline__ float4 philox_normal4(unsigned long long seed, long long row, unsigned key, unsigned blk) {
     const uint4 r = philox4x32_10(make_uint4((unsigned)row, (unsigned)((unsigned long long)row >> 32), key, blk),
                                   make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
     const float u0 = ((r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    const float u1 = ((r.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
     const float u2 = ((r.z >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    const float u3 = ((r.w >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    const float ra = sqrtf(-2.0f * logf(u0)), rb = sqrtf(-2.0f * logf(u2));
+    const float a0 = ((float)(int)(r.y >> 8) - 8388607.5f) * (3.14159265358979f / 8388608.0f);
+    const float a1 = ((float)(int)(r.w >> 8) - 8388607.5f) * (3.14159265358979f / 8388608.0f);
+    const float ra = sqrtf(-2.0f * __logf(u0)), rb = sqrtf(-2.0f * __logf(u2));
     float s0, c0, s1, c1;
-    sincospif(2.0f * u1, &s0, &c0);
-    sincospif(2.0f * u3, &s1, &c1);
+    __sincosf(a0, &s0, &c0);
+    __sincosf(a1, &s1, &c1);
     return make_float4(ra * c0, ra * s0, rb * c1, rb * s1);
 }
 

@@ -440,20 +440,22 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
     if (FC_T2_PROF) asm volatile("mov.u64 %0, %%clock64;" : "=l"(prof_t));
     int trace_n = 0, item_no = 0;
     bool trace_on = false;
+    int cur_step = -1;
     for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
         const int step = dm.T - 1 - (int)(item / tiles_per_step);      // heavy (late) steps first
         const long long tile = item % tiles_per_step;
         trace_on = (item_no++ == 5);
         T2_EV(1)
         T2_TICK(0)   // tail of previous item (output store)
-        __syncthreads();
-        {
+        if (step != cur_step) {              // (CTA-uniform) consecutive items of a CTA almost always share the step
+            __syncthreads();
             const int nw = sizeof(T2Step) / 4;
             const int* s = reinterpret_cast<const int*>(steps + step);
             int* d = reinterpret_cast<int*>(cur);
             for (int i = tid; i < nw; i += kThreadsAll) d[i] = __ldg(s + i);
+            cur_step = step;
+            __syncthreads();
         }
-        __syncthreads();
         const T2Step& ts = *cur;
         const int C = ts.C, c = ts.c, Kin = ts.Kin, Ku = ts.Ku, Wd = ts.Wd, CPd = ts.CPd, Hc = ts.Hc;
 
@@ -543,7 +545,10 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
         }
         // ---- input operand [z (2), cond (C0), prefix (2*step), 0...]: 8-column chunks dealt over the parts ----
         {
-            const float* cp = src_at(a.cond, ag, pt, step);
+            const float* cp = src_at(a.cond, ag, pt, step) - 2;
+            const float* pf = src_at(a.prefix, ag, pt, 0);
+            const long long pst = a.prefix.st;
+            const int c0e = 2 + dm.C0;
             for (int k0 = x.part * 8; k0 < Kin; k0 += 8 * NPARTS) {
                 float v[8];
 #pragma unroll
@@ -551,8 +556,8 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
                     const int col = k0 + i;
                     float val = 0.0f;
                     if (col < 2) val = col == 0 ? z0 : z1;
-                    else if (col < 2 + dm.C0) val = __ldg(cp + (col - 2));
-                    else if (col < c) { const int e = col - 2 - dm.C0; val = __ldg(src_at(a.prefix, ag, pt, e >> 1) + (e & 1)); }
+                    else if (col < c0e) val = __ldg(cp + col);
+                    else if (col < c) { const int e = col - c0e; val = __ldg(pf + (long long)(e >> 1) * pst + (e & 1)); }
                     v[i] = clamp_h(val);
                 }
                 uint32_t hi[4], lo[4];
@@ -620,7 +625,7 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
                         for (int i = 0; i < 8; ++i) {
                             if (d0 + i < C) {
                                 const float m = mu[i] + bias_mu[d0 + i], l = ls[i] + bias_ls[d0 + i];
-                                u[i] = clamp_h(fmaf(expf(l), e[i], m));
+                                u[i] = clamp_h(fmaf(__expf(l), e[i], m));
                                 p_ls += l;
                                 p_e2 = fmaf(e[i], e[i], p_e2);
                             }
@@ -656,7 +661,7 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
                             const float2 hf = __half22float2(h2), lf = __half22float2(l2);
                             const float u = (i & 1) ? hf.y + lf.y : hf.x + lf.x;
                             const float m = mu[i] + bias_mu[d0 + i], l = ls[i] + bias_ls[d0 + i];
-                            const float df = (u - m) * expf(-l);
+                            const float df = (u - m) * __expf(-l);
                             p_q = fmaf(df, df, p_q);
                             p_ls += l;
                         }
