@@ -66,6 +66,41 @@ __device__ __noinline__ float4 philox_normal4(unsigned long long seed, long long
     return make_float4(ra * c0, ra * s0, rb * c1, rb * s1);
 }
 
+// 8 normals for counter blocks (blk, blk + 1): the two Philox streams and Box-Muller pairs are independent, so the
+// compiler interleaves them (the single-stream version is latency-bound: 10 serial rounds).  Same values as two calls
+// of philox_normal4.
+struct Normal8 { float4 a, b; };
+__device__ __noinline__ Normal8 philox_normal8(unsigned long long seed, long long row, unsigned key, unsigned blk) {
+    float out[8];
+    uint4 c0 = make_uint4((unsigned)row, (unsigned)((unsigned long long)row >> 32), key, blk), c1 = c0;
+    c1.w = blk + 1u;
+    uint2 k0 = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const unsigned h00 = __umulhi(0xD2511F53u, c0.x), l00 = 0xD2511F53u * c0.x, h01 = __umulhi(0xCD9E8D57u, c0.z), l01 = 0xCD9E8D57u * c0.z;
+        const unsigned h10 = __umulhi(0xD2511F53u, c1.x), l10 = 0xD2511F53u * c1.x, h11 = __umulhi(0xCD9E8D57u, c1.z), l11 = 0xCD9E8D57u * c1.z;
+        c0 = make_uint4(h01 ^ c0.y ^ k0.x, l01, h00 ^ c0.w ^ k0.y, l00);
+        c1 = make_uint4(h11 ^ c1.y ^ k0.x, l11, h10 ^ c1.w ^ k0.y, l10);
+        k0.x += 0x9E3779B9u;
+        k0.y += 0xBB67AE85u;
+    }
+    const unsigned rr[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const float u = ((rr[2 * p] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const float ang = ((float)(int)(rr[2 * p + 1] >> 8) - 8388607.5f) * (3.14159265358979f / 8388608.0f);
+        const float rad = sqrtf(-2.0f * __logf(u));
+        float s, c;
+        __sincosf(ang, &s, &c);
+        out[2 * p] = rad * c;
+        out[2 * p + 1] = rad * s;
+    }
+    Normal8 r;
+    r.a = make_float4(out[0], out[1], out[2], out[3]);
+    r.b = make_float4(out[4], out[5], out[6], out[7]);
+    return r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // register-tiled layer: thread tile 4 rows x 8 outputs; two independent problems per call
 // (s_net | t_net, or shift_net | log_scale_net) so all 256 threads have work.

@@ -231,8 +231,9 @@ __device__ __forceinline__ void tanh_acc2(float& x0, float& x1) {
     const float y0 = e0 + 1.0f, y1 = e1 + 1.0f;
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y0 * y1));
-    x0 = fmaf(-2.0f * y1, r, 1.0f);
-    x1 = fmaf(-2.0f * y0, r, 1.0f);
+    r *= -2.0f;
+    x0 = fmaf(y1, r, 1.0f);
+    x1 = fmaf(y0, r, 1.0f);
 }
 __device__ __forceinline__ float tanh_acc(float x) {
     float e;
@@ -616,9 +617,8 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
 #pragma unroll
                             for (int i = 0; i < 8; ++i) if (d0 + i < C) e[i] = __ldg(ep + i);
                         } else if (!(FC_T2_ABLATE & 8)) {
-                            const float4 g0 = philox_normal4(a.seed, n, (unsigned)step, (unsigned)(d0 >> 2));
-                            const float4 g1 = philox_normal4(a.seed, n, (unsigned)step, (unsigned)(d0 >> 2) + 1u);
-                            e[0] = g0.x; e[1] = g0.y; e[2] = g0.z; e[3] = g0.w; e[4] = g1.x; e[5] = g1.y; e[6] = g1.z; e[7] = g1.w;
+                            const Normal8 g = philox_normal8(a.seed, n, (unsigned)step, (unsigned)(d0 >> 2));
+                            e[0] = g.a.x; e[1] = g.a.y; e[2] = g.a.z; e[3] = g.a.w; e[4] = g.b.x; e[5] = g.b.y; e[6] = g.b.z; e[7] = g.b.w;
                         }
                         tmem_wait_ld();
 #pragma unroll
