@@ -340,15 +340,30 @@ int launch_density(fc_handle* h, RowArgs a, Mode mode, int precision, cudaStream
         return 0;
     }
     if (precision != FC_PREC_FP32) return fail(h, "unknown precision %d", precision);
-    const size_t smem = smem_bytes_fp32(h->dims, kR, false);
+    // 64-row tiles normally; models too wide for that (e.g. HIDDEN_SIZE 256) fall back to 32-row tiles
+    const bool wide = (int)smem_bytes_fp32(h->dims, 64, false) > h->smem_optin;
+    const int R = wide ? 32 : 64;
+    const size_t smem = smem_bytes_fp32(h->dims, R, false);
+    const long long rtiles = (a.N + R - 1) / R;
+    if (rtiles > 0x7fffffffLL) return fail(h, "too many rows (%lld)", a.N);
     if (mode == MODE_SEPARATE) {
-        if (prep_kernel(h, k_separate_fp32<kR>, smem)) return 1;
-        dim3 grid((unsigned)tiles, (unsigned)T);
-        k_separate_fp32<kR><<<grid, kThreads, smem, stream>>>(h->d_plans, h->d_wbuf, a, h->dims);
+        dim3 grid((unsigned)rtiles, (unsigned)T);
+        if (wide) {
+            if (prep_kernel(h, k_separate_fp32<32>, smem)) return 1;
+            k_separate_fp32<32><<<grid, kThreads, smem, stream>>>(h->d_plans, h->d_wbuf, a, h->dims);
+        } else {
+            if (prep_kernel(h, k_separate_fp32<64>, smem)) return 1;
+            k_separate_fp32<64><<<grid, kThreads, smem, stream>>>(h->d_plans, h->d_wbuf, a, h->dims);
+        }
     } else {
-        if (prep_kernel(h, k_sequential_fp32<kR>, smem)) return 1;
-        dim3 grid((unsigned)tiles, (unsigned)(T - a.seq_jlo));
-        k_sequential_fp32<kR><<<grid, kThreads, smem, stream>>>(h->d_plans, h->d_wbuf, a, h->dims);
+        dim3 grid((unsigned)rtiles, (unsigned)(T - a.seq_jlo));
+        if (wide) {
+            if (prep_kernel(h, k_sequential_fp32<32>, smem)) return 1;
+            k_sequential_fp32<32><<<grid, kThreads, smem, stream>>>(h->d_plans, h->d_wbuf, a, h->dims);
+        } else {
+            if (prep_kernel(h, k_sequential_fp32<64>, smem)) return 1;
+            k_sequential_fp32<64><<<grid, kThreads, smem, stream>>>(h->d_plans, h->d_wbuf, a, h->dims);
+        }
     }
     h->launches++;
     FC_CUDA(h, cudaGetLastError());
@@ -460,11 +475,18 @@ extern "C" int fc_sample_with_log_prob(fc_handle* h, const float* base_pos, cons
     a.eps = eps; a.eps_rs = h->E; a.z0 = z0; a.seed = seed;
     a.N = B * S; a.PPA = S; a.K = 1;
     SampleOut o{seq, log_prob, ldjs, base_lp};
-    const long long tiles = (a.N + kR - 1) / kR;
+    const bool wide = (int)smem_bytes_fp32(h->dims, 64, true) > h->smem_optin;
+    const int R = wide ? 32 : 64;
+    const long long tiles = (a.N + R - 1) / R;
     if (tiles > 0x7fffffffLL) return fail(h, "too many rows");
-    const size_t smem = smem_bytes_fp32(h->dims, kR, true);
-    if (prep_kernel(h, k_sample_fp32<kR>, smem)) return 1;
-    k_sample_fp32<kR><<<(unsigned)tiles, kThreads, smem, (cudaStream_t)stream>>>(h->d_plans, h->d_wbuf, a, h->dims, o);
+    const size_t smem = smem_bytes_fp32(h->dims, R, true);
+    if (wide) {
+        if (prep_kernel(h, k_sample_fp32<32>, smem)) return 1;
+        k_sample_fp32<32><<<(unsigned)tiles, kThreads, smem, (cudaStream_t)stream>>>(h->d_plans, h->d_wbuf, a, h->dims, o);
+    } else {
+        if (prep_kernel(h, k_sample_fp32<64>, smem)) return 1;
+        k_sample_fp32<64><<<(unsigned)tiles, kThreads, smem, (cudaStream_t)stream>>>(h->d_plans, h->d_wbuf, a, h->dims, o);
+    }
     h->launches++;
     FC_CUDA(h, cudaGetLastError());
     return 0;

@@ -215,17 +215,26 @@ def make_case(ref, name, spec, seed, agents, grid_n, S, lo=-3.0, hi=3.0):
     print(name, {k: v.shape for k, v in out.items() if hasattr(v, "shape")}, os.path.getsize(path) // 1024, "KiB")
 
 
+CASES = {
+    # default ETH model (config 1 shapes, small row counts so the fixture stays small)
+    "default_eth": dict(spec=synth.FlowSpec(), seed=0, agents=8, grid_n=6, S=64),
+    # odd shapes: exercises padding / genericity of the fp32 path (Optuna ranges, main.py:222-229)
+    "odd_small": dict(spec=synth.FlowSpec(pred_len=5, cond_size=9, hidden_size=40, n_hidden=1, n_blocks=2), seed=10, agents=5, grid_n=5, S=48),
+    # deeper chain (config 5 knobs at reduced width): n_blocks 6
+    "deep_blocks": dict(spec=synth.FlowSpec(pred_len=4, cond_size=16, hidden_size=64, n_hidden=2, n_blocks=6), seed=20, agents=4, grid_n=4, S=32),
+    # config 5 stress knobs: 2x coupling layers, 256-wide conditioner MLPs (short chain so the fixture stays small)
+    "stress_wide": dict(spec=synth.FlowSpec(pred_len=3, cond_size=16, hidden_size=256, n_hidden=2, n_blocks=6), seed=30, agents=3, grid_n=4, S=32),
+}
+
+
 def main():
     ref = import_reference()
     torch.set_num_threads(4)
-    # default ETH model (config 1 shapes, small row counts so the fixture stays small)
-    make_case(ref, "default_eth", synth.FlowSpec(), seed=0, agents=8, grid_n=6, S=64)
-    # odd shapes: exercises padding / genericity of the fp32 path (Optuna ranges, main.py:222-229)
-    make_case(ref, "odd_small", synth.FlowSpec(pred_len=5, cond_size=9, hidden_size=40, n_hidden=1, n_blocks=2),
-              seed=10, agents=5, grid_n=5, S=48)
-    # deeper chain (config 5 knobs at reduced width): n_blocks 6
-    make_case(ref, "deep_blocks", synth.FlowSpec(pred_len=4, cond_size=16, hidden_size=64, n_hidden=2, n_blocks=6),
-              seed=20, agents=4, grid_n=4, S=32)
+    only = sys.argv[1:]
+    for name, kw in CASES.items():
+        if only and name not in only:
+            continue
+        make_case(ref, name, kw["spec"], seed=kw["seed"], agents=kw["agents"], grid_n=kw["grid_n"], S=kw["S"])
 
 
 if __name__ == "__main__":
