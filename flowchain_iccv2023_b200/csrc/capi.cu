@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -13,6 +14,7 @@
 #include "kernels_fp32.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_tc2.cuh"
+#include "kernels_tc3.cuh"
 #include "plan.h"
 
 #ifndef FC_T2_PARTS
@@ -39,6 +41,8 @@ struct fc_handle {
     unsigned char* d_t2img[2] = {nullptr, nullptr};
     fc::T2Step* d_t2steps[2] = {nullptr, nullptr};
     fc::T2Dims t2dims[2]{};
+    std::vector<fc::T2Step> t2steps_host[2];
+    int tc_kernel = 3;                // 3: two resident tiles per CTA (kernels_tc3.cuh), 2: one tile (kernels_tc2.cuh)
     float* d_upd = nullptr;           // rapid update: per-(agent, chunk) partial sums
     size_t upd_floats = 0;
     float* d_scratch = nullptr;       // K>1 importance-sample staging
@@ -109,6 +113,7 @@ extern "C" int fc_create(fc_handle** out, const fc_model_desc* desc, int device)
     h->desc = *desc;
     h->device = device;
     h->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (const char* e = getenv("FLOWCHAIN_TC_KERNEL")) h->tc_kernel = atoi(e) == 2 ? 2 : 3;   // development switch
     h->num_sms = prop.multiProcessorCount;
     *out = h;
     return 0;
@@ -277,6 +282,7 @@ extern "C" int fc_load_weights(fc_handle* h, const float* blob, size_t n_floats,
         std::vector<unsigned char> img2;
         std::vector<fc::T2Step> st2;
         fc::tc2_pack(d, plans, tcsrc, i == 0 ? 3 : 1, img2, st2, h->t2dims[i], h->smem_optin);
+        h->t2steps_host[i] = st2;
         FC_CUDA(h, cudaFree(h->d_t2img[i])); h->d_t2img[i] = nullptr;
         FC_CUDA(h, cudaFree(h->d_t2steps[i])); h->d_t2steps[i] = nullptr;
         if (h->t2dims[i].supported) {
@@ -334,6 +340,12 @@ int launch_density(fc_handle* h, RowArgs a, Mode mode, int precision, cudaStream
         if (mode != MODE_SEPARATE) return fail(h, "the tensor-core path implements the per-step density only");
         std::string msg;
         const int i = precision == FC_PREC_F16X3 ? 0 : 1;
+        if (h->tc_kernel == 3) {
+            int rc3 = i == 0 ? fc::tc3_launch_separate<3>(h->t2dims[0], h->t2steps_host[0], h->d_t2steps[0], h->d_t2img[0], a, h->num_sms, h->smem_optin, stream, &h->launches, &msg)
+                             : fc::tc3_launch_separate<1>(h->t2dims[1], h->t2steps_host[1], h->d_t2steps[1], h->d_t2img[1], a, h->num_sms, h->smem_optin, stream, &h->launches, &msg);
+            if (rc3) return fail(h, "%s", msg.c_str());
+            return 0;
+        }
         int rc = i == 0 ? fc::tc2_launch_separate<3, FC_T2_PARTS>(h->t2dims[0], h->d_t2steps[0], h->d_t2img[0], a, h->num_sms, h->smem_optin, stream, &h->launches, &msg)
                         : fc::tc2_launch_separate<1, FC_T2_PARTS>(h->t2dims[1], h->d_t2steps[1], h->d_t2img[1], a, h->num_sms, h->smem_optin, stream, &h->launches, &msg);
         if (rc) return fail(h, "%s", msg.c_str());

@@ -52,6 +52,7 @@ struct T2Dims {
     int32_t slot_bytes, nslots;
     int32_t T, C0;
     int32_t supported;
+    int32_t step_hi;         // a launch covers steps step_hi, step_hi-1, ... (heavy first); set by the launcher
 };
 
 
@@ -443,7 +444,7 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
     bool trace_on = false;
     int cur_step = -1;
     for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int step = dm.T - 1 - (int)(item / tiles_per_step);      // heavy (late) steps first
+        const int step = dm.step_hi - (int)(item / tiles_per_step);    // heavy (late) steps first
         const long long tile = item % tiles_per_step;
         trace_on = (item_no++ == 5);
         T2_EV(1)
@@ -755,8 +756,10 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
 }
 
 template <int NPASS, int NPARTS>
-inline int tc2_launch_separate(const T2Dims& dm, const T2Step* d_steps, const unsigned char* d_img, const RowArgs& a, int num_sms,
-                               int smem_optin, cudaStream_t stream, uint64_t* launches, std::string* msg) {
+inline int tc2_launch_separate(T2Dims dm, const T2Step* d_steps, const unsigned char* d_img, const RowArgs& a, int num_sms,
+                               int smem_optin, cudaStream_t stream, uint64_t* launches, std::string* msg, int step_lo = 0, int step_hi = -1) {
+    if (step_hi < 0) step_hi = dm.T - 1;
+    dm.step_hi = step_hi;
     if (!dm.supported || d_img == nullptr) {
         *msg = "the tensor-core path does not support this model shape (needs hidden_size % 16 == 0, hidden_size <= 96, "
                "2*(cond_size + 2*pred_len) <= 96); use FC_PREC_FP32";
@@ -767,7 +770,7 @@ inline int tc2_launch_separate(const T2Dims& dm, const T2Step* d_steps, const un
     cudaError_t e = cudaFuncSetAttribute(k_separate_tc2<NPASS, NPARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { *msg = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return 1; }
     const long long tiles = (a.N + 127) / 128;
-    const long long items = tiles * dm.T;
+    const long long items = tiles * (step_hi - step_lo + 1);
     const int grid = (int)(items < num_sms ? items : num_sms);
     k_separate_tc2<NPASS, NPARTS><<<grid, NPARTS * 128 + 96, smem, stream>>>(d_steps, d_img, a, dm, tiles, items);
     (*launches)++;

@@ -1,0 +1,531 @@
+// kernels_tc3.cuh -- f16x3 / f16 tensor-core per-step density with TWO resident 128-row tiles per CTA.
+//
+// Same arithmetic as kernels_tc2.cuh (split-fp16 operands, tcgen05.mma, fp32 accumulate; see there), re-organised so
+// that two independent tiles share one SM: tensor memory can hold only one tile when every operand lives in it
+// (480 of 512 columns), so here the HIDDEN-layer operands go to shared memory (SS-mode MMA, canonical K-major tiles
+// written by the epilogue) and tensor memory keeps just the accumulators and the two narrow first-layer operands
+// ([z|w, y] and [u, mx], TS-mode) -- 256 columns per tile.  Two groups of 8 epilogue warps each own a tile and run
+// the unchanged per-tile schedule; they share the TMA weight ring (one chunk feeds both tiles: half the L2 traffic
+// per row) and the two MMA-issuer warps (one per net, serving tile 0 then tile 1 for every net-layer).  The groups'
+// epilogues overlap each other and the other tile's MMAs, which hides the MMA -> epilogue -> MMA latency chain that
+// bounds the single-tile kernel.
+#pragma once
+#include "kernels_tc2.cuh"
+
+namespace fc {
+
+// tensor-memory column map of one tile (256 columns per tile)
+constexpr uint32_t kT3Acc0 = 0, kT3Acc1 = 80;            // fp32 accumulators of net 0 / 1 (N <= 80)
+constexpr uint32_t kT3InHi = 160, kT3InLo = 184;         // [z|w, cond, prefix] operand, K <= 48
+constexpr uint32_t kT3UHi = 208, kT3ULo = 232;           // [u, mx] operand, K <= 48
+constexpr uint32_t kT3TileCols = 256;
+constexpr int kT3Threads = 16 * 32 + 96;                  // 2 x 8 compute warps, producer, 2 issuers
+constexpr int kT3Header = 16384;                          // barriers, step table, 2 x row-partial buffers
+
+struct T3Dims {
+    int32_t slot_bytes;      // ring slot (>= largest chunk of the launched steps), multiple of 128
+    int32_t nslots_log2;     // ring depth (1 -> 2 slots, 2 -> 4 slots)
+    int32_t Wmax;            // widest hidden operand of the launched steps (64 or 80): shared-memory operand stride
+    int32_t T, C0;
+    int32_t step_lo, step_hi;   // inclusive range of steps this launch covers
+};
+
+namespace t3 {
+using namespace tc;
+using namespace t2;
+
+struct Bars3 {
+    uint64_t full[4], empty[4];
+    uint64_t mma_done[2][2];     // [tile][net]
+    uint64_t opnd[2][2];         // [tile][net]
+    uint64_t fin[2];             // [tile]
+};
+
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint32_t* v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
+
+// 8 activated values -> hi / lo fp16 rows of the next layer's shared-memory operand tile
+template <int NPASS, int ACT, bool DOT, bool WRITE>
+__device__ __forceinline__ void epi_chunk3(float* u, int c0, uint32_t bias, uint32_t wlast, uint32_t ohi, uint32_t olo, uint32_t koff, float& dot) {
+    const float4 b0 = lds128(bias + (uint32_t)c0 * 4), b1 = lds128(bias + (uint32_t)c0 * 4 + 16);
+    u[0] += b0.x; u[1] += b0.y; u[2] += b0.z; u[3] += b0.w; u[4] += b1.x; u[5] += b1.y; u[6] += b1.z; u[7] += b1.w;
+    if (ACT == ACT_T) {
+#pragma unroll
+        for (int q = 0; q < 8; q += 2) {
+            if (NPASS == 3) tanh_acc2(u[q], u[q + 1]);
+            else { asm("tanh.approx.f32 %0, %0;" : "+f"(u[q])); asm("tanh.approx.f32 %0, %0;" : "+f"(u[q + 1])); }
+        }
+    } else if (DOT) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) u[q] = fmaxf(u[q], 0.0f);
+    }
+    if (DOT) {
+        const float4 w0 = lds128(wlast + (uint32_t)c0 * 4), w1 = lds128(wlast + (uint32_t)c0 * 4 + 16);
+        dot = fmaf(u[0], w0.x, dot); dot = fmaf(u[1], w0.y, dot); dot = fmaf(u[2], w0.z, dot); dot = fmaf(u[3], w0.w, dot);
+        dot = fmaf(u[4], w1.x, dot); dot = fmaf(u[5], w1.y, dot); dot = fmaf(u[6], w1.z, dot); dot = fmaf(u[7], w1.w, dot);
+    }
+    if (WRITE) {
+        uint32_t hi[4], lo[4];
+        split8<NPASS, ACT == ACT_R>(u, hi, lo);
+        // canonical K-major tile: 8 consecutive K elements of one row = one 16-byte store
+        const uint32_t off = koff + (uint32_t)(c0 >> 3) * 128u;
+        sts128(ohi + off, hi);
+        if (NPASS == 3) sts128(olo + off, lo);
+    }
+}
+
+// koff = (row/8) * (W/8) * 128 + (row%8) * 16 : byte offset of this thread's row inside a [128 x W] canonical tile
+template <int NPASS, int ACT, bool DOT, bool WRITE>
+__device__ __noinline__ float epi_hidden3(uint32_t acc, uint32_t ohi, uint32_t olo, uint32_t bias, uint32_t wlast, int part, int W, uint32_t koff) {
+    float dot = 0.0f;
+#pragma unroll 1
+    for (int c0 = part * 8; c0 < W; c0 += 32) {
+        const int c1 = c0 + 16;
+        float v0[8], v1[8];
+        tmem_ld8(acc + (uint32_t)c0, v0);
+        if (c1 < W) tmem_ld8(acc + (uint32_t)c1, v1);
+        tmem_wait_ld();
+        epi_chunk3<NPASS, ACT, DOT, WRITE>(v0, c0, bias, wlast, ohi, olo, koff, dot);
+        if (c1 < W) epi_chunk3<NPASS, ACT, DOT, WRITE>(v1, c1, bias, wlast, ohi, olo, koff, dot);
+    }
+    return dot;
+}
+
+// per-thread view of its group (tile)
+struct X3 {
+    int row, part, lane, g;
+    uint32_t tb;             // tensor-memory base of the tile incl. this warp's lane quadrant
+    Bars3* bars;
+    uint8_t* slots;
+    int slot_bytes;
+    uint32_t nslots_mask, nslots_log2;
+    uint32_t chunk_it;
+    uint32_t mma_cnt0, mma_cnt1;
+    float* part_buf;         // this group's [4][2][128] row-partial exchange
+    uint32_t h_base;         // shared address of this tile's hidden operand tiles: [net][part(hi,lo)] x h_stride
+    uint32_t h_stride;
+};
+
+__device__ __forceinline__ const uint8_t* slot_ptr3(const X3& x, uint32_t it) { return x.slots + (size_t)(it & x.nslots_mask) * x.slot_bytes; }
+__device__ __forceinline__ void wait_mma3(X3& x, int net) {
+    if (net == 0) { mbar_wait(&x.bars->mma_done[x.g][0], x.mma_cnt0 & 1u); x.mma_cnt0++; }
+    else { mbar_wait(&x.bars->mma_done[x.g][1], x.mma_cnt1 & 1u); x.mma_cnt1++; }
+    tc_fence_after();
+}
+// this warp's tensor-memory accesses and shared-memory operand stores are complete -> tell the issuers
+__device__ __forceinline__ void warp_arrive3(const X3& x, uint64_t* bar) {
+    tmem_wait_ld();
+    tmem_wait_st();
+    fence_async_smem();
+    tc_fence_before();
+    __syncwarp();
+    if (x.lane == 0) mbar_arrive(bar);
+}
+__device__ __forceinline__ float row_sum3(const X3& x, int slot, float v) {
+    x.part_buf[(slot * 2 + x.part) * 128 + x.row] = v;
+    asm volatile("bar.sync %0, 256;" ::"r"(1 + x.g) : "memory");
+    return x.part_buf[(slot * 2) * 128 + x.row] + x.part_buf[(slot * 2 + 1) * 128 + x.row];
+}
+
+}  // namespace t3
+
+template <int NPASS>
+__global__ void __launch_bounds__(kT3Threads, 1)
+k_separate_tc3(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img, RowArgs a, T3Dims dm, long long pairs_per_step,
+               long long total_items) {
+    using namespace tc;
+    using namespace t2;
+    using namespace t3;
+    constexpr int NPARTS = 2;
+    extern __shared__ __align__(128) uint8_t smem_t3[];
+    uint8_t* smem = smem_t3;
+    Bars3* bars = reinterpret_cast<Bars3*>(smem);
+    static_assert(sizeof(Bars3) <= 240, "barrier block");
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + 240);
+    T2Step* cur = reinterpret_cast<T2Step*>(smem + 256);
+    static_assert(sizeof(T2Step) <= 1792, "T2Step must fit the header");
+    float* part_all = reinterpret_cast<float*>(smem + 2048);     // 2 groups x (4 x 2 x 128 floats = 4 KB)
+    const uint32_t h_stride = (uint32_t)(128 * dm.Wmax * 2);       // one [128 x Wmax] fp16 tile
+    uint8_t* hbuf = smem + kT3Header;                              // [tile][net][hi,lo]
+    uint8_t* slots = hbuf + (size_t)8 * h_stride;
+    const uint32_t nslots = 1u << dm.nslots_log2, smask = nslots - 1u;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (uint32_t s = 0; s < nslots; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(&bars->mma_done[t][0], 1);
+            mbar_init(&bars->mma_done[t][1], 1);
+            mbar_init(&bars->opnd[t][0], 8);
+            mbar_init(&bars->opnd[t][1], 8);
+            mbar_init(&bars->fin[t], 8);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 16) tmem_alloc(tslot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tslot, 0);
+
+    X3 x;
+    x.lane = lane; x.g = (warp >> 3) & 1; x.part = (warp >> 2) & 1; x.row = (warp & 3) * 32 + lane;
+    x.tb = tmem_base + (uint32_t)x.g * kT3TileCols + ((uint32_t)((warp & 3) * 32) << 16);
+    x.bars = bars; x.slots = slots; x.slot_bytes = dm.slot_bytes; x.nslots_mask = smask; x.nslots_log2 = (uint32_t)dm.nslots_log2;
+    x.chunk_it = 0; x.mma_cnt0 = 0; x.mma_cnt1 = 0;
+    x.part_buf = part_all + x.g * 1024;
+    x.h_stride = h_stride;
+    x.h_base = smem_u32(hbuf) + (uint32_t)x.g * 4u * h_stride;
+    uint32_t ring_it = 0;
+    uint32_t opnd_c0 = 0, opnd_c1 = 0, fin_c0 = 0, fin_c1 = 0;    // issuers: per-tile phase counters
+    int cur_step = -1;
+
+    for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int step = dm.step_hi - (int)(item / pairs_per_step);    // heavy (late) steps first
+        const long long pair = item % pairs_per_step;
+        if (step != cur_step) {
+            __syncthreads();
+            const int nw = sizeof(T2Step) / 4;
+            const int* s = reinterpret_cast<const int*>(steps + step);
+            int* d = reinterpret_cast<int*>(cur);
+            for (int i = tid; i < nw; i += kT3Threads) d[i] = __ldg(s + i);
+            cur_step = step;
+            __syncthreads();
+        }
+        const T2Step& ts = *cur;
+        const int C = ts.C, c = ts.c, Kin = ts.Kin, Ku = ts.Ku, Wd = ts.Wd, CPd = ts.CPd, Hc = ts.Hc;
+
+        if (warp == 16) {
+            // ===== weight producer =====
+            for (int ci = 0; ci < ts.nchunks; ++ci, ++ring_it) {
+                if (lane == 0) {
+                    const uint32_t slot = ring_it & smask;
+                    mbar_wait(&bars->empty[slot], ((ring_it >> dm.nslots_log2) & 1u) ^ 1u);
+                    mbar_expect_tx(&bars->full[slot], (uint32_t)ts.chunk_bytes[ci]);
+                    bulk_load(slots + (size_t)slot * dm.slot_bytes, img + ts.chunk_off[ci], (uint32_t)ts.chunk_bytes[ci], &bars->full[slot]);
+                }
+                __syncwarp();
+            }
+            continue;
+        }
+
+        if (warp > 16) {
+            // ===== MMA issuers, one per net; every net-layer is issued for tile 0 then tile 1 from the same weight chunk.
+            // First layers read their operand from tensor memory (TS), hidden layers from shared memory (SS). =====
+            const int net = warp - 17;
+            const uint32_t base = ring_it;
+            int prev = -1;
+#pragma unroll 1
+            for (int ci = net; ci < ts.nchunks; ci += 2) {
+                const uint32_t it = base + (uint32_t)ci;
+                mbar_wait(&bars->full[it & smask], (it >> dm.nslots_log2) & 1u);
+                const int w = ts.job_wait[ci], src = ts.job_src[ci], Kp = ts.job_kp[ci], N = ts.job_n[ci];
+                const uint32_t b_hi = smem_u32(slots + (size_t)(it & smask) * dm.slot_bytes);
+                const uint32_t idesc = umma_idesc_f16(128, N), sbo = (uint32_t)(Kp >> 3) * 128u;
+                const uint64_t dhi = umma_desc(b_hi, 128, sbo), dlo = umma_desc(b_hi + (uint32_t)(N * Kp * 2), 128, sbo);
+                const int nk = Kp >> 4;
+                uint32_t leader;
+                asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(leader));
+#pragma unroll 1
+                for (int t = 0; t < 2; ++t) {
+                    const uint32_t tb0 = tmem_base + (uint32_t)t * kT3TileCols;
+                    const uint32_t acc = tb0 + (net ? kT3Acc1 : kT3Acc0);
+                    const uint32_t ta_hi = tb0 + (src == 0 ? kT3InHi : kT3UHi), ta_lo = tb0 + (src == 0 ? kT3InLo : kT3ULo);
+                    const uint32_t sa = smem_u32(hbuf) + (uint32_t)(t * 4 + net * 2) * h_stride;
+                    const uint64_t ahi = umma_desc(sa, 128, sbo), alo = umma_desc(sa + h_stride, 128, sbo);
+                    // ---- critical path: operand of this tile ready -> MMAs -> commit ----
+                    if (w == 3) {
+                        if (t == 0) { mbar_wait(&bars->fin[0], fin_c0 & 1u); fin_c0++; }
+                        else { mbar_wait(&bars->fin[1], fin_c1 & 1u); fin_c1++; }
+                    } else {
+                        if (t == 0) { mbar_wait(&bars->opnd[0][net], opnd_c0 & 1u); opnd_c0++; }
+                        else { mbar_wait(&bars->opnd[1][net], opnd_c1 & 1u); opnd_c1++; }
+                    }
+                    tc_fence_after();
+                    if (leader) {
+                        if (src < 2) {
+#pragma unroll 3
+                            for (int ks = 0; ks < nk; ++ks) umma_ts(acc, ta_hi + ks * 8, dhi + (uint64_t)(ks * 16), idesc, ks > 0 ? 1u : 0u);
+                            if (NPASS == 3) {
+#pragma unroll 3
+                                for (int ks = 0; ks < nk; ++ks) umma_ts(acc, ta_lo + ks * 8, dhi + (uint64_t)(ks * 16), idesc, 1u);
+#pragma unroll 3
+                                for (int ks = 0; ks < nk; ++ks) umma_ts(acc, ta_hi + ks * 8, dlo + (uint64_t)(ks * 16), idesc, 1u);
+                            }
+                        } else {
+#pragma unroll 5
+                            for (int ks = 0; ks < nk; ++ks) umma_bf16(acc, ahi + (uint64_t)(ks * 16), dhi + (uint64_t)(ks * 16), idesc, ks > 0 ? 1u : 0u);
+                            if (NPASS == 3) {
+#pragma unroll 5
+                                for (int ks = 0; ks < nk; ++ks) umma_bf16(acc, alo + (uint64_t)(ks * 16), dhi + (uint64_t)(ks * 16), idesc, 1u);
+#pragma unroll 5
+                                for (int ks = 0; ks < nk; ++ks) umma_bf16(acc, ahi + (uint64_t)(ks * 16), dlo + (uint64_t)(ks * 16), idesc, 1u);
+                            }
+                        }
+                        umma_commit(&bars->mma_done[t][net]);
+                    }
+                    __syncwarp();
+                }
+                if (prev >= 0) mbar_arrive_elect(&bars->empty[(base + (uint32_t)prev) & smask]);
+                prev = ci;
+            }
+            // both tiles' final q-density epilogues done -> the last chunk of this net goes back
+            mbar_wait(&bars->fin[0], fin_c0 & 1u); fin_c0++;
+            mbar_wait(&bars->fin[1], fin_c1 & 1u); fin_c1++;
+            mbar_arrive_elect(&bars->empty[(base + (uint32_t)prev) & smask]);
+            ring_it += (uint32_t)ts.nchunks;
+            continue;
+        }
+
+        // ===== compute groups: group g owns tile 2*pair + g; thread = (row, column part) =====
+        const int g = x.g;
+        long long n = (pair * 2 + g) * 128 + x.row;
+        const bool valid = n < a.N;
+        if (!valid) n = a.N - 1;
+        const long long ag = n / a.PPA, rem = n % a.PPA, pt = rem / a.K;
+        float z0, z1, prev0, prev1, lacc = 0.0f;
+        {
+            const float* xp = src_at(a.x, ag, pt, step);
+            z0 = __ldg(xp); z1 = __ldg(xp + 1);
+            const float* pp = step == 0 ? src_at(a.base, ag, pt, 0) : src_at(a.prefix, ag, pt, step - 1);
+            prev0 = __ldg(pp); prev1 = __ldg(pp + 1);
+        }
+        // byte offset of this row inside a canonical [128 x W] operand tile, for the two hidden widths of the step
+        const uint32_t koff_d = (uint32_t)((x.row >> 3) * (Wd >> 3) * 128 + (x.row & 7) * 16);
+        const uint32_t koff_c = (uint32_t)((x.row >> 3) * (Hc >> 3) * 128 + (x.row & 7) * 16);
+        // ---- input operand [z (2), cond (C0), prefix (2*step), 0...] ----
+        {
+            const float* cp = src_at(a.cond, ag, pt, step) - 2;
+            const float* pf = src_at(a.prefix, ag, pt, 0);
+            const long long pst = a.prefix.st;
+            const int c0e = 2 + dm.C0;
+            for (int k0 = x.part * 8; k0 < Kin; k0 += 8 * NPARTS) {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int col = k0 + i;
+                    float val = 0.0f;
+                    if (col < 2) val = col == 0 ? z0 : z1;
+                    else if (col < c0e) val = __ldg(cp + col);
+                    else if (col < c) { const int e = col - c0e; val = __ldg(pf + (long long)(e >> 1) * pst + (e & 1)); }
+                    v[i] = clamp_h(val);
+                }
+                uint32_t hi[4], lo[4];
+                split8<NPASS, false>(v, hi, lo);
+                tmem_st4(x.tb + kT3InHi + (uint32_t)(k0 >> 1), hi);
+                if (NPASS == 3) tmem_st4(x.tb + kT3InLo + (uint32_t)(k0 >> 1), lo);
+            }
+        }
+        warp_arrive3(x, &bars->fin[g]);
+
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {
+            // ============ density nets (shift | log-scale): two relu layers ============
+#pragma unroll 1
+            for (int l = 0; l < 2; ++l) {
+#pragma unroll 1
+                for (int net = 0; net < 2; ++net) {
+                    const uint32_t bias = smem_u32(slot_ptr3(x, x.chunk_it)) + (uint32_t)((NPASS == 3 ? 2 : 1) * Wd * (l == 0 ? Kin : Wd) * 2);
+                    wait_mma3(x, net);
+                    epi_hidden3<NPASS, ACT_R, false, true>(x.tb + (net ? kT3Acc1 : kT3Acc0), x.h_base + (uint32_t)(net * 2) * h_stride,
+                                                           x.h_base + (uint32_t)(net * 2 + 1) * h_stride, bias, 0u, x.part, Wd, koff_d);
+                    warp_arrive3(x, &bars->opnd[g][net]);
+                    x.chunk_it++;
+                }
+            }
+            // ---- L3 outputs: means in acc0[0,CPd), log-stddevs in acc1[0,CPd) ----
+            const size_t w3 = (size_t)(NPASS == 3 ? 2 : 1) * CPd * Wd * 2;
+            const float* bias_mu = reinterpret_cast<const float*>(slot_ptr3(x, x.chunk_it) + w3);
+            const float* bias_ls = reinterpret_cast<const float*>(slot_ptr3(x, x.chunk_it + 1) + w3);
+            x.chunk_it += 2;
+            wait_mma3(x, 0);
+            wait_mma3(x, 1);
+            if (which == 0) {
+                // sample u = exp(ls) eps + mu (fastpredNF.py:727-733) -> [u, mx] operand; log r = -C/2 log 2pi - sum ls - 1/2 sum eps^2
+                const int m0 = ts.masked_dim[0];
+                float p_ls = 0.0f, p_e2 = 0.0f;
+                for (int d0 = x.part * 8; d0 < Ku; d0 += 8 * NPARTS) {
+                    float u[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) u[i] = 0.0f;
+                    if (d0 < CPd) {
+                        float mu[8], ls[8], e[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) e[i] = 0.0f;
+                        tmem_ld8(x.tb + kT3Acc0 + (uint32_t)d0, mu);
+                        tmem_ld8(x.tb + kT3Acc1 + (uint32_t)d0, ls);
+                        if (a.eps != nullptr) {
+                            const float* ep = a.eps + n * a.eps_rs + ts.eps_off + d0;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) if (d0 + i < C) e[i] = __ldg(ep + i);
+                        } else {
+                            const Normal8 gn = philox_normal8(a.seed, n, (unsigned)step, (unsigned)(d0 >> 2));
+                            e[0] = gn.a.x; e[1] = gn.a.y; e[2] = gn.a.z; e[3] = gn.a.w; e[4] = gn.b.x; e[5] = gn.b.y; e[6] = gn.b.z; e[7] = gn.b.w;
+                        }
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (d0 + i < C) {
+                                const float m = mu[i] + bias_mu[d0 + i], l = ls[i] + bias_ls[d0 + i];
+                                u[i] = clamp_h(fmaf(__expf(l), e[i], m));
+                                p_ls += l;
+                                p_e2 = fmaf(e[i], e[i], p_e2);
+                            }
+                        }
+                    }
+                    if (d0 == (C & ~7)) {        // mx = z * mask of the first coupling sits at columns C, C+1
+#pragma unroll
+                        for (int i = 0; i < 8; i += 2)
+                            if (i == (C & 7)) { u[i] = m0 == 0 ? clamp_h(z0) : 0.0f; u[i + 1] = m0 == 1 ? clamp_h(z1) : 0.0f; }
+                    }
+                    uint32_t hi[4], lo[4];
+                    split8<3, false>(u, hi, lo);     // u is always kept as a hi+lo pair: log q needs it back at full precision
+                    tmem_st4(x.tb + kT3UHi + (uint32_t)(d0 >> 1), hi);
+                    tmem_st4(x.tb + kT3ULo + (uint32_t)(d0 >> 1), lo);
+                }
+                const float s_ls = row_sum3(x, 0, p_ls), s_e2 = row_sum3(x, 1, p_e2);
+                lacc -= (-0.5f * (float)C * kLog2Pi - s_ls) - 0.5f * s_e2;
+            } else {
+                // log q(u | w, y) (fastpredNF.py:713-724), u reconstructed from its hi+lo operand
+                float p_ls = 0.0f, p_q = 0.0f;
+                for (int d0 = x.part * 8; d0 < CPd; d0 += 8 * NPARTS) {
+                    float mu[8], ls[8];
+                    uint32_t uh[4], ul[4];
+                    tmem_ld8(x.tb + kT3Acc0 + (uint32_t)d0, mu);
+                    tmem_ld8(x.tb + kT3Acc1 + (uint32_t)d0, ls);
+                    tmem_ld4(x.tb + kT3UHi + (uint32_t)(d0 >> 1), uh);
+                    tmem_ld4(x.tb + kT3ULo + (uint32_t)(d0 >> 1), ul);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (d0 + i < C) {
+                            const __half2 h2 = *reinterpret_cast<const __half2*>(&uh[i >> 1]), l2 = *reinterpret_cast<const __half2*>(&ul[i >> 1]);
+                            const float2 hf = __half22float2(h2), lf = __half22float2(l2);
+                            const float u = (i & 1) ? hf.y + lf.y : hf.x + lf.x;
+                            const float m = mu[i] + bias_mu[d0 + i], l = ls[i] + bias_ls[d0 + i];
+                            const float df = (u - m) * __expf(-l);
+                            p_q = fmaf(df, df, p_q);
+                            p_ls += l;
+                        }
+                    }
+                }
+                const float s_ls = row_sum3(x, 0, p_ls), s_q = row_sum3(x, 1, p_q);
+                lacc += (-0.5f * (float)C * kLog2Pi - s_ls) - 0.5f * s_q;
+            }
+            warp_arrive3(x, &bars->fin[g]);
+            if (which == 1) break;
+
+            // ============ n_blocks x (masked affine coupling + BatchNorm), forward ============
+#pragma unroll 1
+            for (int b = 0; b < ts.n_blocks; ++b) {
+                const int j = 1 - ts.masked_dim[b];
+                float ps = 0.0f, pt_ = 0.0f, bs = 0.0f, bt = 0.0f;
+#pragma unroll 1
+                for (int l = 0; l <= ts.n_hidden; ++l) {
+                    const bool last = l == ts.n_hidden;
+#pragma unroll 1
+                    for (int net = 0; net < 2; ++net) {
+                        const uint32_t tail = smem_u32(slot_ptr3(x, x.chunk_it)) + (uint32_t)((NPASS == 3 ? 2 : 1) * Hc * (l == 0 ? Ku : Hc) * 2);
+                        x.chunk_it++;
+                        wait_mma3(x, net);
+                        const uint32_t acc = x.tb + (net ? kT3Acc1 : kT3Acc0);
+                        const uint32_t ohi = x.h_base + (uint32_t)(net * 2) * h_stride, olo = ohi + h_stride;
+                        if (!last) {
+                            if (net == 0) epi_hidden3<NPASS, ACT_T, false, true>(acc, ohi, olo, tail, 0u, x.part, Hc, koff_c);
+                            else epi_hidden3<NPASS, ACT_R, false, true>(acc, ohi, olo, tail, 0u, x.part, Hc, koff_c);
+                            warp_arrive3(x, &bars->opnd[g][net]);
+                        } else {
+                            if (net == 0) { ps = epi_hidden3<NPASS, ACT_T, true, false>(acc, ohi, olo, tail, tail + Hc * 4, x.part, Hc, koff_c); bs = lds32(tail + Hc * 8); }
+                            else { pt_ = epi_hidden3<NPASS, ACT_R, true, false>(acc, ohi, olo, tail, tail + Hc * 4, x.part, Hc, koff_c); bt = lds32(tail + Hc * 8); }
+                        }
+                    }
+                }
+                // both nets done: affine update of the unmasked coordinate + BatchNorm (TFCondARFlow.py:360-381, 303-315)
+                const float s = row_sum3(x, 2, ps) + bs, t = row_sum3(x, 3, pt_) + bt;
+                const float log_s = tanhf(s);
+                if (j == 0) z0 = fmaf(z0, expf(log_s), t); else z1 = fmaf(z1, expf(log_s), t);
+                z0 = fmaf(ts.bn_scale[b][0], z0, ts.bn_shift[b][0]);
+                z1 = fmaf(ts.bn_scale[b][1], z1, ts.bn_shift[b][1]);
+                lacc += log_s + ts.bn_ldj[b];
+                const bool more = b + 1 < ts.n_blocks;
+                float p0, p1;
+                uint32_t dst_hi, dst_lo;
+                int owner;
+                if (more) {
+                    const int mn = ts.masked_dim[b + 1];
+                    p0 = mn == 0 ? clamp_h(z0) : 0.0f; p1 = mn == 1 ? clamp_h(z1) : 0.0f;
+                    dst_hi = kT3UHi + (uint32_t)(C >> 1); dst_lo = kT3ULo + (uint32_t)(C >> 1);
+                    owner = (C >> 3) % NPARTS;
+                } else {
+                    p0 = clamp_h(z0); p1 = clamp_h(z1);
+                    dst_hi = kT3InHi; dst_lo = kT3InLo;
+                    owner = 0;
+                }
+                if (x.part == owner) {
+                    const __half2 h = __floats2half2_rn(p0, p1);
+                    const float2 f = __half22float2(h);
+                    const __half2 lo2 = __floats2half2_rn(p0 - f.x, p1 - f.y);
+                    tmem_st1(x.tb + dst_hi, *reinterpret_cast<const uint32_t*>(&h));
+                    tmem_st1(x.tb + dst_lo, *reinterpret_cast<const uint32_t*>(&lo2));
+                }
+                warp_arrive3(x, &bars->fin[g]);
+            }
+        }
+        if (valid && x.part == 0) {
+            const float lp = normal_lp2(z0, z1, prev0, prev1, ts.std[0], ts.std[1]) + lacc;
+            a.out[ag * a.out_sa + rem * a.out_sp + (long long)step * a.out_st] = lp;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 16) tmem_dealloc(tmem_base, 512);
+}
+
+// Launches the steps in groups of equal operand-width class: hidden width <= 64 -> this two-tile kernel (128 KB of
+// operand tiles + a 4-slot weight ring); wider steps (hidden 80: 160 KB of operand tiles leave no room for the ring)
+// -> the single-tile kernel of kernels_tc2.cuh.
+template <int NPASS>
+inline int tc3_launch_separate(const T2Dims& dm2, const std::vector<T2Step>& hsteps, const T2Step* d_steps, const unsigned char* d_img,
+                               const RowArgs& a, int num_sms, int smem_optin, cudaStream_t stream, uint64_t* launches, std::string* msg) {
+    if (!dm2.supported || d_img == nullptr) { *msg = "the tensor-core path does not support this model shape; use FC_PREC_FP32"; return 1; }
+    const int T = dm2.T;
+    const long long tiles = (a.N + 127) / 128, pairs = (tiles + 1) / 2;
+    int lo = 0;
+    while (lo < T) {
+        // group consecutive steps with the same operand-width class
+        auto wclass = [&](int s) { const int w = hsteps[s].Wd > hsteps[s].Hc ? hsteps[s].Wd : hsteps[s].Hc; return w <= 64 ? 64 : 80; };
+        int hi = lo;
+        const int wc = wclass(lo);
+        while (hi + 1 < T && wclass(hi + 1) == wc) ++hi;
+        int slot = 0;
+        for (int s = lo; s <= hi; ++s)
+            for (int ci = 0; ci < hsteps[s].nchunks; ++ci) slot = hsteps[s].chunk_bytes[ci] > slot ? hsteps[s].chunk_bytes[ci] : slot;
+        slot = (slot + 127) / 128 * 128;
+        T3Dims dm{};
+        dm.slot_bytes = slot; dm.Wmax = wc; dm.T = T; dm.C0 = dm2.C0; dm.step_lo = lo; dm.step_hi = hi;
+        const size_t fixed = (size_t)kT3Header + (size_t)8 * 128 * wc * 2;
+        dm.nslots_log2 = 2;      // the issuers hold a chunk until the NEXT job of the same net is issued: >= 3 slots needed
+        const size_t smem = fixed + (size_t)4 * slot;
+        if (smem > (size_t)smem_optin) {
+            // operand tiles of two resident tiles + a 4-deep ring do not fit (hidden width 80): single-tile kernel
+            int rc = tc2_launch_separate<NPASS, 2>(dm2, d_steps, d_img, a, num_sms, smem_optin, stream, launches, msg, lo, hi);
+            if (rc) return rc;
+            lo = hi + 1;
+            continue;
+        }
+        cudaError_t e = cudaFuncSetAttribute(k_separate_tc3<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { *msg = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return 1; }
+        const long long items = pairs * (hi - lo + 1);
+        const int grid = (int)(items < num_sms ? items : num_sms);
+        k_separate_tc3<NPASS><<<grid, kT3Threads, smem, stream>>>(d_steps, d_img, a, dm, pairs, items);
+        (*launches)++;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) { *msg = std::string("k_separate_tc3 launch: ") + cudaGetErrorString(e); return 1; }
+        lo = hi + 1;
+    }
+    return 0;
+}
+
+}  // namespace fc
