@@ -20,7 +20,8 @@ constexpr uint32_t kT3InHi = 160, kT3InLo = 184;         // [z|w, cond, prefix] 
 constexpr uint32_t kT3UHi = 208, kT3ULo = 232;           // [u, mx] operand, K <= 48
 constexpr uint32_t kT3TileCols = 256;
 constexpr int kT3Threads = 16 * 32 + 96;                  // 2 x 8 compute warps, producer, 2 issuers
-constexpr int kT3Header = 16384;                          // barriers, step table, 2 x row-partial buffers
+constexpr int kT3Header = 12288;                          // barriers, step table, row-partial buffers, bias ring
+constexpr int kT3BiasEntry = 768;                         // bytes per (net, job & 3) entry of the bias ring
 
 struct T3Dims {
     int32_t slot_bytes;      // ring slot (>= largest chunk of the launched steps), multiple of 128
@@ -102,7 +103,8 @@ struct X3 {
     uint32_t nslots_mask, nslots_log2;
     uint32_t chunk_it;
     uint32_t mma_cnt0, mma_cnt1;
-    float* part_buf;         // this group's [4][2][128] row-partial exchange
+    float* part_buf;         // this group's [2][2][128] row-partial exchange
+    uint32_t bias_ring;      // shared address of the bias ring: [net][job & 3] x kT3BiasEntry
     uint32_t h_base;         // shared address of this tile's hidden operand tiles: [net][part(hi,lo)] x h_stride
     uint32_t h_stride;
 };
@@ -122,7 +124,7 @@ __device__ __forceinline__ void warp_arrive3(const X3& x, uint64_t* bar) {
     __syncwarp();
     if (x.lane == 0) mbar_arrive(bar);
 }
-__device__ __forceinline__ float row_sum3(const X3& x, int slot, float v) {
+__device__ __forceinline__ float row_sum3(const X3& x, int slot, float v) {      // slot in {0, 1}
     x.part_buf[(slot * 2 + x.part) * 128 + x.row] = v;
     asm volatile("bar.sync %0, 256;" ::"r"(1 + x.g) : "memory");
     return x.part_buf[(slot * 2) * 128 + x.row] + x.part_buf[(slot * 2 + 1) * 128 + x.row];
@@ -145,7 +147,8 @@ k_separate_tc3(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
     uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + 240);
     T2Step* cur = reinterpret_cast<T2Step*>(smem + 256);
     static_assert(sizeof(T2Step) <= 1792, "T2Step must fit the header");
-    float* part_all = reinterpret_cast<float*>(smem + 2048);     // 2 groups x (4 x 2 x 128 floats = 4 KB)
+    float* part_all = reinterpret_cast<float*>(smem + 2048);     // 2 groups x (2 x 2 x 128 floats = 2 KB)
+    uint8_t* bias_ring = smem + 6144;                              // [net][job & 3] x 768 B: fp32 tails of the weight chunks
     const uint32_t h_stride = (uint32_t)(128 * dm.Wmax * 2);       // one [128 x Wmax] fp16 tile
     uint8_t* hbuf = smem + kT3Header;                              // [tile][net][hi,lo]
     uint8_t* slots = hbuf + (size_t)8 * h_stride;
@@ -174,7 +177,8 @@ k_separate_tc3(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
     x.tb = tmem_base + (uint32_t)x.g * kT3TileCols + ((uint32_t)((warp & 3) * 32) << 16);
     x.bars = bars; x.slots = slots; x.slot_bytes = dm.slot_bytes; x.nslots_mask = smask; x.nslots_log2 = (uint32_t)dm.nslots_log2;
     x.chunk_it = 0; x.mma_cnt0 = 0; x.mma_cnt1 = 0;
-    x.part_buf = part_all + x.g * 1024;
+    x.part_buf = part_all + x.g * 512;
+    x.bias_ring = smem_u32(bias_ring);
     x.h_stride = h_stride;
     x.h_base = smem_u32(hbuf) + (uint32_t)x.g * 4u * h_stride;
     uint32_t ring_it = 0;
@@ -215,13 +219,22 @@ k_separate_tc3(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
             // First layers read their operand from tensor memory (TS), hidden layers from shared memory (SS). =====
             const int net = warp - 17;
             const uint32_t base = ring_it;
-            int prev = -1;
 #pragma unroll 1
             for (int ci = net; ci < ts.nchunks; ci += 2) {
                 const uint32_t it = base + (uint32_t)ci;
                 mbar_wait(&bars->full[it & smask], (it >> dm.nslots_log2) & 1u);
                 const int w = ts.job_wait[ci], src = ts.job_src[ci], Kp = ts.job_kp[ci], N = ts.job_n[ci];
-                const uint32_t b_hi = smem_u32(slots + (size_t)(it & smask) * dm.slot_bytes);
+                const uint8_t* chunk = slots + (size_t)(it & smask) * dm.slot_bytes;
+                const uint32_t b_hi = smem_u32(chunk);
+                {   // the fp32 tail (biases, last-row vector) moves to the bias ring so that the weight slot can be handed
+                    // back as soon as the MMAs that read it complete (tcgen05.commit -> empty), not after the epilogue
+                    const int tiles_b = (NPASS == 3 ? 2 : 1) * N * Kp * 2;
+                    const int n16 = (ts.chunk_bytes[ci] - tiles_b) >> 4;
+                    const float4* srcp = reinterpret_cast<const float4*>(chunk + tiles_b);
+                    float4* dstp = reinterpret_cast<float4*>(bias_ring + (size_t)(net * 4 + ((it >> 1) & 3)) * kT3BiasEntry);
+                    for (int q = lane; q < n16; q += 32) dstp[q] = srcp[q];
+                    __syncwarp();
+                }
                 const uint32_t idesc = umma_idesc_f16(128, N), sbo = (uint32_t)(Kp >> 3) * 128u;
                 const uint64_t dhi = umma_desc(b_hi, 128, sbo), dlo = umma_desc(b_hi + (uint32_t)(N * Kp * 2), 128, sbo);
                 const int nk = Kp >> 4;
@@ -264,16 +277,14 @@ k_separate_tc3(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
                             }
                         }
                         umma_commit(&bars->mma_done[t][net]);
+                        if (t == 1) umma_commit(&bars->empty[it & smask]);   // both tiles' MMAs done -> slot free
                     }
                     __syncwarp();
                 }
-                if (prev >= 0) mbar_arrive_elect(&bars->empty[(base + (uint32_t)prev) & smask]);
-                prev = ci;
             }
-            // both tiles' final q-density epilogues done -> the last chunk of this net goes back
+            // consume the final `fin` phase of both tiles (the q-density epilogues) to stay in step with the groups
             mbar_wait(&bars->fin[0], fin_c0 & 1u); fin_c0++;
             mbar_wait(&bars->fin[1], fin_c1 & 1u); fin_c1++;
-            mbar_arrive_elect(&bars->empty[(base + (uint32_t)prev) & smask]);
             ring_it += (uint32_t)ts.nchunks;
             continue;
         }
@@ -326,7 +337,7 @@ k_separate_tc3(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
             for (int l = 0; l < 2; ++l) {
 #pragma unroll 1
                 for (int net = 0; net < 2; ++net) {
-                    const uint32_t bias = smem_u32(slot_ptr3(x, x.chunk_it)) + (uint32_t)((NPASS == 3 ? 2 : 1) * Wd * (l == 0 ? Kin : Wd) * 2);
+                    const uint32_t bias = x.bias_ring + (uint32_t)(net * 4 + ((x.chunk_it >> 1) & 3)) * kT3BiasEntry;
                     wait_mma3(x, net);
                     epi_hidden3<NPASS, ACT_R, false, true>(x.tb + (net ? kT3Acc1 : kT3Acc0), x.h_base + (uint32_t)(net * 2) * h_stride,
                                                            x.h_base + (uint32_t)(net * 2 + 1) * h_stride, bias, 0u, x.part, Wd, koff_d);
@@ -335,9 +346,8 @@ k_separate_tc3(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
                 }
             }
             // ---- L3 outputs: means in acc0[0,CPd), log-stddevs in acc1[0,CPd) ----
-            const size_t w3 = (size_t)(NPASS == 3 ? 2 : 1) * CPd * Wd * 2;
-            const float* bias_mu = reinterpret_cast<const float*>(slot_ptr3(x, x.chunk_it) + w3);
-            const float* bias_ls = reinterpret_cast<const float*>(slot_ptr3(x, x.chunk_it + 1) + w3);
+            const float* bias_mu = reinterpret_cast<const float*>(bias_ring + (size_t)(0 * 4 + ((x.chunk_it >> 1) & 3)) * kT3BiasEntry);
+            const float* bias_ls = reinterpret_cast<const float*>(bias_ring + (size_t)(1 * 4 + ((x.chunk_it >> 1) & 3)) * kT3BiasEntry);
             x.chunk_it += 2;
             wait_mma3(x, 0);
             wait_mma3(x, 1);
@@ -426,7 +436,7 @@ k_separate_tc3(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
                     const bool last = l == ts.n_hidden;
 #pragma unroll 1
                     for (int net = 0; net < 2; ++net) {
-                        const uint32_t tail = smem_u32(slot_ptr3(x, x.chunk_it)) + (uint32_t)((NPASS == 3 ? 2 : 1) * Hc * (l == 0 ? Ku : Hc) * 2);
+                        const uint32_t tail = x.bias_ring + (uint32_t)(net * 4 + ((x.chunk_it >> 1) & 3)) * kT3BiasEntry;
                         x.chunk_it++;
                         wait_mma3(x, net);
                         const uint32_t acc = x.tb + (net ? kT3Acc1 : kT3Acc0);
@@ -442,7 +452,7 @@ k_separate_tc3(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
                     }
                 }
                 // both nets done: affine update of the unmasked coordinate + BatchNorm (TFCondARFlow.py:360-381, 303-315)
-                const float s = row_sum3(x, 2, ps) + bs, t = row_sum3(x, 3, pt_) + bt;
+                const float s = row_sum3(x, 0, ps) + bs, t = row_sum3(x, 1, pt_) + bt;
                 const float log_s = tanhf(s);
                 if (j == 0) z0 = fmaf(z0, expf(log_s), t); else z1 = fmaf(z1, expf(log_s), t);
                 z0 = fmaf(ts.bn_scale[b][0], z0, ts.bn_shift[b][0]);
@@ -506,10 +516,11 @@ inline int tc3_launch_separate(const T2Dims& dm2, const std::vector<T2Step>& hst
         T3Dims dm{};
         dm.slot_bytes = slot; dm.Wmax = wc; dm.T = T; dm.C0 = dm2.C0; dm.step_lo = lo; dm.step_hi = hi;
         const size_t fixed = (size_t)kT3Header + (size_t)8 * 128 * wc * 2;
-        dm.nslots_log2 = 2;      // the issuers hold a chunk until the NEXT job of the same net is issued: >= 3 slots needed
-        const size_t smem = fixed + (size_t)4 * slot;
+        // a weight slot is handed back by the tcgen05.commit of the MMAs that read it, so 2 slots (one per net) already
+        // pipeline; 4 when they fit
+        dm.nslots_log2 = (fixed + (size_t)4 * slot <= (size_t)smem_optin) ? 2 : 1;
+        const size_t smem = fixed + ((size_t)1 << dm.nslots_log2) * slot;
         if (smem > (size_t)smem_optin) {
-            // operand tiles of two resident tiles + a 4-deep ring do not fit (hidden width 80): single-tile kernel
             int rc = tc2_launch_separate<NPASS, 2>(dm2, d_steps, d_img, a, num_sms, smem_optin, stream, launches, msg, lo, hi);
             if (rc) return rc;
             lo = hi + 1;
