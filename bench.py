@@ -35,9 +35,11 @@ UNIT = "evals/s"
 
 
 def ncu_traffic(precision: str):
-    """DRAM bytes (read + write) of ONE launch of the dominant kernel, from the committed `ncu --set full` capture of
-    this same command (profiles/): None when no capture exists for the chosen precision."""
-    name = {"f16x3": "r01_ncu_full_k_separate_tc2_f16x3.csv", "fp32": None}.get(precision)
+    """DRAM bytes (read + write) of ONE pass of the dominant kernel, from the committed `ncu --set full` capture of this
+    same command (profiles/).  The f16x3 kernel (k_separate_tc3) covers the 12 steps with two launches (one per weight
+    width class), so the capture holds two rows and the traffic of a pass is their sum.  None when no capture exists
+    for the chosen precision."""
+    name = {"f16x3": "r01_ncu_full_k_separate_tc3_f16x3.csv", "fp32": None}.get(precision)
     path = os.path.join(ROOT, "profiles", name) if name else None
     if not path or not os.path.exists(path):
         return None
@@ -45,16 +47,17 @@ def ncu_traffic(precision: str):
     rows = list(csv.reader(open(path)))
     if len(rows) < 3:
         return None
-    hdr, unit, val = rows[0], rows[1], rows[2]
+    hdr, unit = rows[0], rows[1]
     tot = 0.0
-    for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-        if key not in hdr:
-            return None
-        i = hdr.index(key)
-        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit[i], None)
-        if scale is None:
-            return None
-        tot += float(val[i]) * scale
+    for val in rows[2:]:
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            if key not in hdr:
+                return None
+            i = hdr.index(key)
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit[i], None)
+            if scale is None:
+                return None
+            tot += float(val[i]) * scale
     return tot
 
 
@@ -312,7 +315,8 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(args.precision) if (A == 64 and n == 256) else None,
-                         "traffic_note": "dram read+write bytes of one launch, ncu --set full capture in profiles/ (algorithmic output: %d B)" % (A * G * T * 4),
+                         "traffic_note": "dram read+write bytes of one pass (all launches of the dominant kernel), ncu --set full capture in profiles/ (algorithmic output: %d B)" % (A * G * T * 4),
+                         "launches_per_pass": int(launches) // max(args.steps, 1),
                          "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
                          "kernel_ms": kern_ms, "algorithmic_flops_per_launch": flops_launch},
         }

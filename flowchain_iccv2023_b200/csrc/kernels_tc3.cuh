@@ -48,8 +48,7 @@ __device__ __forceinline__ void sts128(uint32_t saddr, const uint32_t* v) {
 
 // 8 activated values -> hi / lo fp16 rows of the next layer's shared-memory operand tile
 template <int NPASS, int ACT, bool DOT, bool WRITE>
-__device__ __forceinline__ void epi_chunk3(float* u, int c0, uint32_t bias, uint32_t wlast, uint32_t ohi, uint32_t olo, uint32_t koff, float& dot) {
-    const float4 b0 = lds128(bias + (uint32_t)c0 * 4), b1 = lds128(bias + (uint32_t)c0 * 4 + 16);
+__device__ __forceinline__ void epi_chunk3(float* u, int c0, const float4 b0, const float4 b1, uint32_t wlast, uint32_t ohi, uint32_t olo, uint32_t koff, float& dot) {
     u[0] += b0.x; u[1] += b0.y; u[2] += b0.z; u[3] += b0.w; u[4] += b1.x; u[5] += b1.y; u[6] += b1.z; u[7] += b1.w;
     if (ACT == ACT_T) {
 #pragma unroll
@@ -86,9 +85,12 @@ __device__ __noinline__ float epi_hidden3(uint32_t acc, uint32_t ohi, uint32_t o
         float v0[8], v1[8];
         tmem_ld8(acc + (uint32_t)c0, v0);
         if (c1 < W) tmem_ld8(acc + (uint32_t)c1, v1);
+        // the bias loads ride under the tensor-memory load latency (the ring entry has 16 floats of slack past W)
+        const float4 b00 = lds128(bias + (uint32_t)c0 * 4), b01 = lds128(bias + (uint32_t)c0 * 4 + 16);
+        const float4 b10 = lds128(bias + (uint32_t)c1 * 4), b11 = lds128(bias + (uint32_t)c1 * 4 + 16);
         tmem_wait_ld();
-        epi_chunk3<NPASS, ACT, DOT, WRITE>(v0, c0, bias, wlast, ohi, olo, koff, dot);
-        if (c1 < W) epi_chunk3<NPASS, ACT, DOT, WRITE>(v1, c1, bias, wlast, ohi, olo, koff, dot);
+        epi_chunk3<NPASS, ACT, DOT, WRITE>(v0, c0, b00, b01, wlast, ohi, olo, koff, dot);
+        if (c1 < W) epi_chunk3<NPASS, ACT, DOT, WRITE>(v1, c1, b10, b11, wlast, ohi, olo, koff, dot);
     }
     return dot;
 }
