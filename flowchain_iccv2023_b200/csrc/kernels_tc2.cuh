@@ -56,6 +56,8 @@ struct T2Dims {
 };
 
 
+constexpr float kTanhPrescale = 2.885390081777927f;     // 2 log2(e)
+
 // Packs the fp16 image: per step, per net-layer one chunk = [hi tile][lo tile (npass 3)][fp32 tail].
 inline void tc2_pack(const fc_model_desc& d, const std::vector<StepPlan>& plans, const std::vector<TcStepSrc>& src, int npass,
                      std::vector<unsigned char>& img, std::vector<T2Step>& steps, T2Dims& dm, int smem_optin) {
@@ -121,8 +123,18 @@ inline void tc2_pack(const fc_model_desc& d, const std::vector<StepPlan>& plans,
                         memcpy(extra.data(), s.cpl_W[b][net][sp.n_hidden + 1] + (size_t)j * H, (size_t)H * 4);
                         extra[H] = s.cpl_b[b][net][sp.n_hidden + 1][j];
                     }
-                    chunk(s.cpl_W[b][net][l], s.cpl_b[b][net][l], H, l == 0 ? c : H, H, l == 0 ? ts.Ku : H,
-                          extra.empty() ? nullptr : extra.data(), (int)extra.size());
+                    const float* Wl = s.cpl_W[b][net][l];
+                    const float* bl = s.cpl_b[b][net][l];
+                    const int Kl = l == 0 ? c : H;
+                    std::vector<float> Ws, bs;
+                    if (npass == 3 && net == 0) {   // s-net layers feed tanh = 1 - 2/(1 + 2^(2 log2(e) x)): fold the factor into W, b
+                        Ws.assign(Wl, Wl + (size_t)H * Kl);
+                        bs.assign(bl, bl + H);
+                        for (float& v : Ws) v *= kTanhPrescale;
+                        for (float& v : bs) v *= kTanhPrescale;
+                        Wl = Ws.data(); bl = bs.data();
+                    }
+                    chunk(Wl, bl, H, Kl, H, l == 0 ? ts.Ku : H, extra.empty() ? nullptr : extra.data(), (int)extra.size());
                 }
         }
         dens(1);
@@ -224,11 +236,11 @@ __device__ __forceinline__ void split8(const float* a, uint32_t* hi, uint32_t* l
 }
 // tanh(x) = 1 - 2 / (1 + e^{2x}), |err| ~ 5e-7 (MUFU.TANH itself is only 2^-11 accurate).  Two values share ONE
 // reciprocal (r = 1/(y0 y1), 1/y0 = r y1, 1/y1 = r y0): 1.5 MUFU ops per value instead of 2.
+// The inputs arrive PRE-SCALED by 2 log2(e) (tc2_pack folds the factor into the s-net weights and biases).
 __device__ __forceinline__ void tanh_acc2(float& x0, float& x1) {
     float e0, e1;
-    const float c = 2.885390081777927f;                        // 2 log2(e)
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(x0, 15.0f) * c));   // clamp: keeps y0*y1 finite, tanh(15) == 1
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(x1, 15.0f) * c));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(x0, 43.0f)));   // clamp: keeps y0*y1 finite, tanh(43 / 2.885) == 1
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(x1, 43.0f)));
     const float y0 = e0 + 1.0f, y1 = e1 + 1.0f;
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y0 * y1));

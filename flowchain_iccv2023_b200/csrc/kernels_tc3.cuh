@@ -387,9 +387,10 @@ k_separate_tc3(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
                         }
                     }
                     if (d0 == (C & ~7)) {        // mx = z * mask of the first coupling sits at columns C, C+1
+                        const int cm = C & 7;
+                        const float a0 = m0 == 0 ? clamp_h(z0) : 0.0f, a1 = m0 == 1 ? clamp_h(z1) : 0.0f;
 #pragma unroll
-                        for (int i = 0; i < 8; i += 2)
-                            if (i == (C & 7)) { u[i] = m0 == 0 ? clamp_h(z0) : 0.0f; u[i + 1] = m0 == 1 ? clamp_h(z1) : 0.0f; }
+                        for (int i = 0; i < 8; i += 2) { u[i] = i == cm ? a0 : u[i]; u[i + 1] = i == cm ? a1 : u[i + 1]; }   // selects: keeps u[] in registers
                     }
                     uint32_t hi[4], lo[4];
                     split8<3, false>(u, hi, lo);     // u is always kept as a hi+lo pair: log q needs it back at full precision
