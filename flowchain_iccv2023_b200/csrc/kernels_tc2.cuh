@@ -46,6 +46,9 @@ struct T2Step {
     uint8_t job_wait[kT2MaxChunks], job_rel[kT2MaxChunks], job_net[kT2MaxChunks], job_src[kT2MaxChunks];  // src: 0 IN, 1 U, 2 H[net]
     uint8_t job_kp[kT2MaxChunks], job_n[kT2MaxChunks];      // Kp, N in elements
     uint8_t tail_rel, pad1[3];                                // chunks handed back after the last `fin`
+    // 1: the chunk ends with a [N x 16] fp16 bias tile (columns 0..2 = the bias as three fp16 pieces) that the two-tile
+    // kernel multiplies by a constant ones tile, so the bias arrives inside the accumulator (kernels_tc3.cuh)
+    uint8_t job_fold[kT2MaxChunks];
 };
 
 struct T2Dims {
@@ -58,7 +61,10 @@ struct T2Dims {
 
 constexpr float kTanhPrescale = 2.885390081777927f;     // 2 log2(e)
 
-// Packs the fp16 image: per step, per net-layer one chunk = [hi tile][lo tile (npass 3)][fp32 tail].
+// hidden layers up to this width carry a bias tile (wider ones would not fit the two-tile kernel's weight slots)
+constexpr int kFoldMaxN = 64;
+
+// Packs the fp16 image: per step, per net-layer one chunk = [hi tile][lo tile (npass 3)][fp32 tail][bias tile (folded)].
 inline void tc2_pack(const fc_model_desc& d, const std::vector<StepPlan>& plans, const std::vector<TcStepSrc>& src, int npass,
                      std::vector<unsigned char>& img, std::vector<T2Step>& steps, T2Dims& dm, int smem_optin) {
     img.clear();
@@ -87,7 +93,7 @@ inline void tc2_pack(const fc_model_desc& d, const std::vector<StepPlan>& plans,
         ts.std[0] = sp.std[0]; ts.std[1] = sp.std[1];
         int nch = 0;
         // one chunk: W [rows x K] (row-major, as nn.Linear.weight) -> canonical K-major tiles + tail
-        auto chunk = [&](const float* W, const float* bias, int rows, int K, int rows_pad, int Kp, const float* extra, int n_extra) {
+        auto chunk = [&](const float* W, const float* bias, int rows, int K, int rows_pad, int Kp, const float* extra, int n_extra, bool fold) {
             while (img.size() % 128) img.push_back(0);
             ts.chunk_off[nch] = (int32_t)img.size();
             for (int part = 0; part < (npass == 3 ? 2 : 1); ++part) {
@@ -100,6 +106,18 @@ inline void tc2_pack(const fc_model_desc& d, const std::vector<StepPlan>& plans,
             memcpy(img.data() + o, bias, (size_t)rows * 4);
             if (n_extra) memcpy(img.data() + o + (size_t)rows_pad * 4, extra, (size_t)n_extra * 4);
             while (img.size() % 16) img.push_back(0);
+            fold = fold && rows_pad <= kFoldMaxN;
+            if (fold) {      // bias = p0 + p1 + p2 with fp16 pieces (33 mantissa bits): exact through the fp32 accumulate
+                std::vector<float> bm((size_t)rows_pad * 16, 0.0f);
+                for (int r = 0; r < rows; ++r) {
+                    const float p0 = h2f(f2h(bias[r])), p1 = h2f(f2h(bias[r] - p0)), p2 = h2f(f2h(bias[r] - p0 - p1));
+                    bm[(size_t)r * 16] = p0; bm[(size_t)r * 16 + 1] = p1; bm[(size_t)r * 16 + 2] = p2;
+                }
+                const size_t ob = img.size();
+                img.resize(ob + (size_t)rows_pad * 16 * 2);
+                pack_kmajor_f16(img.data() + ob, bm.data(), rows_pad, 16, rows_pad, 16, 0);
+            }
+            ts.job_fold[nch] = fold ? 1 : 0;
             ts.chunk_bytes[nch] = (int32_t)(img.size() - ts.chunk_off[nch]);
             dm.slot_bytes = ts.chunk_bytes[nch] > dm.slot_bytes ? ts.chunk_bytes[nch] : dm.slot_bytes;
             ++nch;
@@ -110,7 +128,7 @@ inline void tc2_pack(const fc_model_desc& d, const std::vector<StepPlan>& plans,
             const int kp[3] = {ts.Kin, ts.Wd, ts.Wd}, np[3] = {ts.Wd, ts.Wd, ts.CPd};
             for (int l = 0; l < 3; ++l)
                 for (int net = 0; net < 2; ++net)
-                    chunk(s.dens_W[which][net][l], s.dens_b[which][net][l], dims[l + 1], dims[l], np[l], kp[l], nullptr, 0);
+                    chunk(s.dens_W[which][net][l], s.dens_b[which][net][l], dims[l + 1], dims[l], np[l], kp[l], nullptr, 0, l < 2);
         };
         dens(0);
         for (int b = 0; b < sp.n_blocks; ++b) {
@@ -134,7 +152,7 @@ inline void tc2_pack(const fc_model_desc& d, const std::vector<StepPlan>& plans,
                         for (float& v : bs) v *= kTanhPrescale;
                         Wl = Ws.data(); bl = bs.data();
                     }
-                    chunk(Wl, bl, H, Kl, H, l == 0 ? ts.Ku : H, extra.empty() ? nullptr : extra.data(), (int)extra.size());
+                    chunk(Wl, bl, H, Kl, H, l == 0 ? ts.Ku : H, extra.empty() ? nullptr : extra.data(), (int)extra.size(), true);
                 }
         }
         dens(1);

@@ -20,7 +20,8 @@ constexpr uint32_t kT3InHi = 160, kT3InLo = 184;         // [z|w, cond, prefix] 
 constexpr uint32_t kT3UHi = 208, kT3ULo = 232;           // [u, mx] operand, K <= 48
 constexpr uint32_t kT3TileCols = 256;
 constexpr int kT3Threads = 16 * 32 + 96;                  // 2 x 8 compute warps, producer, 2 issuers
-constexpr int kT3Header = 12288;                          // barriers, step table, row-partial buffers, bias ring
+constexpr int kT3OnesOff = 12288;                         // constant [128 x 16] fp16 tile, columns 0..2 = 1 (bias fold)
+constexpr int kT3Header = 16384;                          // barriers, step table, row-partial buffers, bias ring, ones tile
 constexpr int kT3BiasEntry = 768;                         // bytes per (net, job & 3) entry of the bias ring
 
 struct T3Dims {
@@ -47,9 +48,9 @@ __device__ __forceinline__ void sts128(uint32_t saddr, const uint32_t* v) {
 }
 
 // 8 activated values -> hi / lo fp16 rows of the next layer's shared-memory operand tile
-template <int NPASS, int ACT, bool DOT, bool WRITE>
+template <int NPASS, int ACT, bool DOT, bool WRITE, bool BIAS>
 __device__ __forceinline__ void epi_chunk3(float* u, int c0, const float4 b0, const float4 b1, uint32_t wlast, uint32_t ohi, uint32_t olo, uint32_t koff, float& dot) {
-    u[0] += b0.x; u[1] += b0.y; u[2] += b0.z; u[3] += b0.w; u[4] += b1.x; u[5] += b1.y; u[6] += b1.z; u[7] += b1.w;
+    if (BIAS) { u[0] += b0.x; u[1] += b0.y; u[2] += b0.z; u[3] += b0.w; u[4] += b1.x; u[5] += b1.y; u[6] += b1.z; u[7] += b1.w; }
     if (ACT == ACT_T) {
 #pragma unroll
         for (int q = 0; q < 8; q += 2) {
@@ -76,7 +77,8 @@ __device__ __forceinline__ void epi_chunk3(float* u, int c0, const float4 b0, co
 }
 
 // koff = (row/8) * (W/8) * 128 + (row%8) * 16 : byte offset of this thread's row inside a [128 x W] canonical tile
-template <int NPASS, int ACT, bool DOT, bool WRITE>
+// BIAS = false: the bias is already inside the accumulator (folded chunk, see the issuer)
+template <int NPASS, int ACT, bool DOT, bool WRITE, bool BIAS>
 __device__ __noinline__ float epi_hidden3(uint32_t acc, uint32_t ohi, uint32_t olo, uint32_t bias, uint32_t wlast, int part, int W, uint32_t koff) {
     float dot = 0.0f;
 #pragma unroll 1
@@ -86,11 +88,14 @@ __device__ __noinline__ float epi_hidden3(uint32_t acc, uint32_t ohi, uint32_t o
         tmem_ld8(acc + (uint32_t)c0, v0);
         if (c1 < W) tmem_ld8(acc + (uint32_t)c1, v1);
         // the bias loads ride under the tensor-memory load latency (the ring entry has 16 floats of slack past W)
-        const float4 b00 = lds128(bias + (uint32_t)c0 * 4), b01 = lds128(bias + (uint32_t)c0 * 4 + 16);
-        const float4 b10 = lds128(bias + (uint32_t)c1 * 4), b11 = lds128(bias + (uint32_t)c1 * 4 + 16);
+        float4 b00 = make_float4(0.f, 0.f, 0.f, 0.f), b01 = b00, b10 = b00, b11 = b00;
+        if (BIAS) {
+            b00 = lds128(bias + (uint32_t)c0 * 4); b01 = lds128(bias + (uint32_t)c0 * 4 + 16);
+            b10 = lds128(bias + (uint32_t)c1 * 4); b11 = lds128(bias + (uint32_t)c1 * 4 + 16);
+        }
         tmem_wait_ld();
-        epi_chunk3<NPASS, ACT, DOT, WRITE>(v0, c0, b00, b01, wlast, ohi, olo, koff, dot);
-        if (c1 < W) epi_chunk3<NPASS, ACT, DOT, WRITE>(v1, c1, b10, b11, wlast, ohi, olo, koff, dot);
+        epi_chunk3<NPASS, ACT, DOT, WRITE, BIAS>(v0, c0, b00, b01, wlast, ohi, olo, koff, dot);
+        if (c1 < W) epi_chunk3<NPASS, ACT, DOT, WRITE, BIAS>(v1, c1, b10, b11, wlast, ohi, olo, koff, dot);
     }
     return dot;
 }
@@ -134,164 +139,183 @@ __device__ __forceinline__ float row_sum3(const X3& x, int slot, float v) {     
 
 }  // namespace t3
 
-template <int NPASS>
-__global__ void __launch_bounds__(kT3Threads, 1)
-k_separate_tc3(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img, RowArgs a, T3Dims dm, long long pairs_per_step,
-               long long total_items) {
-    using namespace tc;
-    using namespace t2;
-    using namespace t3;
-    constexpr int NPARTS = 2;
-    extern __shared__ __align__(128) uint8_t smem_t3[];
-    uint8_t* smem = smem_t3;
-    Bars3* bars = reinterpret_cast<Bars3*>(smem);
-    static_assert(sizeof(Bars3) <= 240, "barrier block");
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + 240);
-    T2Step* cur = reinterpret_cast<T2Step*>(smem + 256);
-    static_assert(sizeof(T2Step) <= 1792, "T2Step must fit the header");
-    float* part_all = reinterpret_cast<float*>(smem + 2048);     // 2 groups x (2 x 2 x 128 floats = 2 KB)
-    uint8_t* bias_ring = smem + 6144;                              // [net][job & 3] x 768 B: fp32 tails of the weight chunks
-    const uint32_t h_stride = (uint32_t)(128 * dm.Wmax * 2);       // one [128 x Wmax] fp16 tile
-    uint8_t* hbuf = smem + kT3Header;                              // [tile][net][hi,lo]
-    uint8_t* slots = hbuf + (size_t)8 * h_stride;
-    const uint32_t nslots = 1u << dm.nslots_log2, smask = nslots - 1u;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) {
-        for (uint32_t s = 0; s < nslots; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-        for (int t = 0; t < 2; ++t) {
-            mbar_init(&bars->mma_done[t][0], 1);
-            mbar_init(&bars->mma_done[t][1], 1);
-            mbar_init(&bars->opnd[t][0], 8);
-            mbar_init(&bars->opnd[t][1], 8);
-            mbar_init(&bars->fin[t], 8);
-        }
-        mbar_fence_init();
-    }
-    if (warp == 16) tmem_alloc(tslot, 512);
-    tc_fence_before();
+namespace t3 {
+using namespace tc;
+using namespace t2;
+// Shared-memory map of the kernel and the per-launch constants every role needs.
+struct T3Smem {
+    Bars3* bars;
+    T2Step* cur;
+    uint8_t *bias_ring, *hbuf, *slots, *ones;
+    float* part_all;
+    uint32_t h_stride, smask;
+};
+__device__ __forceinline__ T3Smem t3_smem(uint8_t* smem, const T3Dims& dm) {
+    T3Smem m;
+    m.bars = reinterpret_cast<Bars3*>(smem);
+    m.cur = reinterpret_cast<T2Step*>(smem + 256);
+    m.part_all = reinterpret_cast<float*>(smem + 2048);          // 2 groups x (2 x 2 x 128 floats = 2 KB)
+    m.bias_ring = smem + 6144;                                     // [net][job & 3] x 768 B: fp32 tails of the weight chunks
+    m.ones = smem + kT3OnesOff;
+    m.h_stride = (uint32_t)(128 * dm.Wmax * 2);                    // one [128 x Wmax] fp16 tile
+    m.hbuf = smem + kT3Header;                                     // [tile][net][hi,lo]
+    m.slots = m.hbuf + (size_t)8 * m.h_stride;
+    m.smask = (1u << dm.nslots_log2) - 1u;
+    return m;
+}
+// All roles walk the same item sequence; when the step changes the whole CTA reloads the step table.
+__device__ __forceinline__ void t3_load_step(const T2Step* steps, int step, T2Step* cur, int tid) {
     __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tslot, 0);
+    const int nw = sizeof(T2Step) / 4;
+    const int* s = reinterpret_cast<const int*>(steps + step);
+    int* d = reinterpret_cast<int*>(cur);
+    for (int i = tid; i < nw; i += kT3Threads) d[i] = __ldg(s + i);
+    __syncthreads();
+}
+#define T3_ITEM_LOOP_BEGIN                                                                          \
+    int cur_step = -1;                                                                              \
+    for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {                      \
+        const int step = dm.step_hi - (int)(item / pairs_per_step); /* heavy (late) steps first */  \
+        const long long pair = item % pairs_per_step;                                               \
+        (void)pair;                                                                                 \
+        if (step != cur_step) { t3_load_step(steps, step, m.cur, (int)threadIdx.x); cur_step = step; } \
+        const T2Step& ts = *m.cur;
+#define T3_ITEM_LOOP_END }
 
-    X3 x;
-    x.lane = lane; x.g = (warp >> 3) & 1; x.part = (warp >> 2) & 1; x.row = (warp & 3) * 32 + lane;
-    x.tb = tmem_base + (uint32_t)x.g * kT3TileCols + ((uint32_t)((warp & 3) * 32) << 16);
-    x.bars = bars; x.slots = slots; x.slot_bytes = dm.slot_bytes; x.nslots_mask = smask; x.nslots_log2 = (uint32_t)dm.nslots_log2;
-    x.chunk_it = 0; x.mma_cnt0 = 0; x.mma_cnt1 = 0;
-    x.part_buf = part_all + x.g * 512;
-    x.bias_ring = smem_u32(bias_ring);
-    x.h_stride = h_stride;
-    x.h_base = smem_u32(hbuf) + (uint32_t)x.g * 4u * h_stride;
+// ===== weight producer (one warp): streams the step's chunks through the ring =====
+__device__ __forceinline__ void t3_producer(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img, const T3Dims& dm,
+                                         long long pairs_per_step, long long total_items, uint8_t* smem) {
+    const T3Smem m = t3_smem(smem, dm);
+    Bars3* bars = m.bars;
+    uint8_t* slots = m.slots;
+    const uint32_t smask = m.smask;
+    const int lane = threadIdx.x & 31;
     uint32_t ring_it = 0;
-    uint32_t opnd_c0 = 0, opnd_c1 = 0, fin_c0 = 0, fin_c1 = 0;    // issuers: per-tile phase counters
-    int cur_step = -1;
-
-    for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int step = dm.step_hi - (int)(item / pairs_per_step);    // heavy (late) steps first
-        const long long pair = item % pairs_per_step;
-        if (step != cur_step) {
-            __syncthreads();
-            const int nw = sizeof(T2Step) / 4;
-            const int* s = reinterpret_cast<const int*>(steps + step);
-            int* d = reinterpret_cast<int*>(cur);
-            for (int i = tid; i < nw; i += kT3Threads) d[i] = __ldg(s + i);
-            cur_step = step;
-            __syncthreads();
+    T3_ITEM_LOOP_BEGIN
+        for (int ci = 0; ci < ts.nchunks; ++ci, ++ring_it) {
+            if (lane == 0) {
+                const uint32_t slot = ring_it & smask;
+                mbar_wait(&bars->empty[slot], ((ring_it >> dm.nslots_log2) & 1u) ^ 1u);
+                mbar_expect_tx(&bars->full[slot], (uint32_t)ts.chunk_bytes[ci]);
+                bulk_load(slots + (size_t)slot * dm.slot_bytes, img + ts.chunk_off[ci], (uint32_t)ts.chunk_bytes[ci], &bars->full[slot]);
+            }
+            __syncwarp();
         }
-        const T2Step& ts = *cur;
-        const int C = ts.C, c = ts.c, Kin = ts.Kin, Ku = ts.Ku, Wd = ts.Wd, CPd = ts.CPd, Hc = ts.Hc;
+    T3_ITEM_LOOP_END
+}
 
-        if (warp == 16) {
-            // ===== weight producer =====
-            for (int ci = 0; ci < ts.nchunks; ++ci, ++ring_it) {
-                if (lane == 0) {
-                    const uint32_t slot = ring_it & smask;
-                    mbar_wait(&bars->empty[slot], ((ring_it >> dm.nslots_log2) & 1u) ^ 1u);
-                    mbar_expect_tx(&bars->full[slot], (uint32_t)ts.chunk_bytes[ci]);
-                    bulk_load(slots + (size_t)slot * dm.slot_bytes, img + ts.chunk_off[ci], (uint32_t)ts.chunk_bytes[ci], &bars->full[slot]);
+// ===== MMA issuers, one warp per net; every net-layer is issued for tile 0 then tile 1 from the same weight chunk.
+// First layers read their operand from tensor memory (TS), hidden layers from shared memory (SS). =====
+template <int NPASS>
+__device__ __forceinline__ void t3_issuer(const T2Step* __restrict__ steps, const T3Dims& dm, long long pairs_per_step, long long total_items,
+                                       uint8_t* smem, uint32_t tmem_base, int net) {
+    const T3Smem m = t3_smem(smem, dm);
+    Bars3* bars = m.bars;
+    uint8_t *slots = m.slots, *hbuf = m.hbuf, *bias_ring = m.bias_ring;
+    const uint32_t smask = m.smask, h_stride = m.h_stride;
+    const int lane = threadIdx.x & 31;
+    uint32_t ring_it = 0;
+    uint32_t opnd_c0 = 0, opnd_c1 = 0, fin_c0 = 0, fin_c1 = 0;    // per-tile phase counters
+    T3_ITEM_LOOP_BEGIN
+        const uint32_t base = ring_it;
+#pragma unroll 1
+        for (int ci = net; ci < ts.nchunks; ci += 2) {
+            const uint32_t it = base + (uint32_t)ci;
+            mbar_wait(&bars->full[it & smask], (it >> dm.nslots_log2) & 1u);
+            const int w = ts.job_wait[ci], src = ts.job_src[ci], Kp = ts.job_kp[ci], N = ts.job_n[ci];
+            const bool fold = ts.job_fold[ci] != 0;
+            const uint8_t* chunk = slots + (size_t)(it & smask) * dm.slot_bytes;
+            const uint32_t b_hi = smem_u32(chunk);
+            {   // the fp32 tail (biases, last-row vector) moves to the bias ring so that the weight slot can be handed
+                // back as soon as the MMAs that read it complete (tcgen05.commit -> empty), not after the epilogue
+                const int tiles_b = (NPASS == 3 ? 2 : 1) * N * Kp * 2;
+                const int n16 = (ts.chunk_bytes[ci] - tiles_b - (fold ? N * 32 : 0)) >> 4;
+                const float4* srcp = reinterpret_cast<const float4*>(chunk + tiles_b);
+                float4* dstp = reinterpret_cast<float4*>(bias_ring + (size_t)(net * 4 + ((it >> 1) & 3)) * kT3BiasEntry);
+                for (int q = lane; q < n16; q += 32) dstp[q] = srcp[q];
+                __syncwarp();
+            }
+            const uint32_t idesc = umma_idesc_f16(128, N), sbo = (uint32_t)(Kp >> 3) * 128u;
+            const uint64_t dhi = umma_desc(b_hi, 128, sbo), dlo = umma_desc(b_hi + (uint32_t)(N * Kp * 2), 128, sbo);
+            const int nk = Kp >> 4;
+            // folded bias: acc = ones[128 x 16] * bias_tile[N x 16]^T first, everything else accumulates on top
+            const uint64_t d_ones = umma_desc(smem_u32(m.ones), 128, 256u);
+            const uint64_t d_bias = umma_desc(b_hi + (uint32_t)(ts.chunk_bytes[ci] - N * 32), 128, 256u);
+            const uint32_t acc0 = fold ? 1u : 0u;
+            uint32_t leader;
+            asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(leader));
+#pragma unroll 1
+            for (int t = 0; t < 2; ++t) {
+                const uint32_t tb0 = tmem_base + (uint32_t)t * kT3TileCols;
+                const uint32_t acc = tb0 + (net ? kT3Acc1 : kT3Acc0);
+                const uint32_t ta_hi = tb0 + (src == 0 ? kT3InHi : kT3UHi), ta_lo = tb0 + (src == 0 ? kT3InLo : kT3ULo);
+                const uint32_t sa = smem_u32(hbuf) + (uint32_t)(t * 4 + net * 2) * h_stride;
+                const uint64_t ahi = umma_desc(sa, 128, sbo), alo = umma_desc(sa + h_stride, 128, sbo);
+                // ---- critical path: operand of this tile ready -> MMAs -> commit ----
+                if (w == 3) {
+                    if (t == 0) { mbar_wait(&bars->fin[0], fin_c0 & 1u); fin_c0++; }
+                    else { mbar_wait(&bars->fin[1], fin_c1 & 1u); fin_c1++; }
+                } else {
+                    if (t == 0) { mbar_wait(&bars->opnd[0][net], opnd_c0 & 1u); opnd_c0++; }
+                    else { mbar_wait(&bars->opnd[1][net], opnd_c1 & 1u); opnd_c1++; }
+                }
+                tc_fence_after();
+                if (leader) {
+                    if (fold) umma_bf16(acc, d_ones, d_bias, idesc, 0u);
+                    if (src < 2) {
+#pragma unroll 3
+                        for (int ks = 0; ks < nk; ++ks) umma_ts(acc, ta_hi + ks * 8, dhi + (uint64_t)(ks * 16), idesc, ks > 0 ? 1u : acc0);
+                        if (NPASS == 3) {
+#pragma unroll 3
+                            for (int ks = 0; ks < nk; ++ks) umma_ts(acc, ta_lo + ks * 8, dhi + (uint64_t)(ks * 16), idesc, 1u);
+#pragma unroll 3
+                            for (int ks = 0; ks < nk; ++ks) umma_ts(acc, ta_hi + ks * 8, dlo + (uint64_t)(ks * 16), idesc, 1u);
+                        }
+                    } else {
+#pragma unroll 5
+                        for (int ks = 0; ks < nk; ++ks) umma_bf16(acc, ahi + (uint64_t)(ks * 16), dhi + (uint64_t)(ks * 16), idesc, ks > 0 ? 1u : acc0);
+                        if (NPASS == 3) {
+#pragma unroll 5
+                            for (int ks = 0; ks < nk; ++ks) umma_bf16(acc, alo + (uint64_t)(ks * 16), dhi + (uint64_t)(ks * 16), idesc, 1u);
+#pragma unroll 5
+                            for (int ks = 0; ks < nk; ++ks) umma_bf16(acc, ahi + (uint64_t)(ks * 16), dlo + (uint64_t)(ks * 16), idesc, 1u);
+                        }
+                    }
+                    umma_commit(&bars->mma_done[t][net]);
+                    if (t == 1) umma_commit(&bars->empty[it & smask]);   // both tiles' MMAs done -> slot free
                 }
                 __syncwarp();
             }
-            continue;
         }
+        // consume the final `fin` phase of both tiles (the q-density epilogues) to stay in step with the groups
+        mbar_wait(&bars->fin[0], fin_c0 & 1u); fin_c0++;
+        mbar_wait(&bars->fin[1], fin_c1 & 1u); fin_c1++;
+        ring_it += (uint32_t)ts.nchunks;
+    T3_ITEM_LOOP_END
+}
 
-        if (warp > 16) {
-            // ===== MMA issuers, one per net; every net-layer is issued for tile 0 then tile 1 from the same weight chunk.
-            // First layers read their operand from tensor memory (TS), hidden layers from shared memory (SS). =====
-            const int net = warp - 17;
-            const uint32_t base = ring_it;
-#pragma unroll 1
-            for (int ci = net; ci < ts.nchunks; ci += 2) {
-                const uint32_t it = base + (uint32_t)ci;
-                mbar_wait(&bars->full[it & smask], (it >> dm.nslots_log2) & 1u);
-                const int w = ts.job_wait[ci], src = ts.job_src[ci], Kp = ts.job_kp[ci], N = ts.job_n[ci];
-                const uint8_t* chunk = slots + (size_t)(it & smask) * dm.slot_bytes;
-                const uint32_t b_hi = smem_u32(chunk);
-                {   // the fp32 tail (biases, last-row vector) moves to the bias ring so that the weight slot can be handed
-                    // back as soon as the MMAs that read it complete (tcgen05.commit -> empty), not after the epilogue
-                    const int tiles_b = (NPASS == 3 ? 2 : 1) * N * Kp * 2;
-                    const int n16 = (ts.chunk_bytes[ci] - tiles_b) >> 4;
-                    const float4* srcp = reinterpret_cast<const float4*>(chunk + tiles_b);
-                    float4* dstp = reinterpret_cast<float4*>(bias_ring + (size_t)(net * 4 + ((it >> 1) & 3)) * kT3BiasEntry);
-                    for (int q = lane; q < n16; q += 32) dstp[q] = srcp[q];
-                    __syncwarp();
-                }
-                const uint32_t idesc = umma_idesc_f16(128, N), sbo = (uint32_t)(Kp >> 3) * 128u;
-                const uint64_t dhi = umma_desc(b_hi, 128, sbo), dlo = umma_desc(b_hi + (uint32_t)(N * Kp * 2), 128, sbo);
-                const int nk = Kp >> 4;
-                uint32_t leader;
-                asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(leader));
-#pragma unroll 1
-                for (int t = 0; t < 2; ++t) {
-                    const uint32_t tb0 = tmem_base + (uint32_t)t * kT3TileCols;
-                    const uint32_t acc = tb0 + (net ? kT3Acc1 : kT3Acc0);
-                    const uint32_t ta_hi = tb0 + (src == 0 ? kT3InHi : kT3UHi), ta_lo = tb0 + (src == 0 ? kT3InLo : kT3ULo);
-                    const uint32_t sa = smem_u32(hbuf) + (uint32_t)(t * 4 + net * 2) * h_stride;
-                    const uint64_t ahi = umma_desc(sa, 128, sbo), alo = umma_desc(sa + h_stride, 128, sbo);
-                    // ---- critical path: operand of this tile ready -> MMAs -> commit ----
-                    if (w == 3) {
-                        if (t == 0) { mbar_wait(&bars->fin[0], fin_c0 & 1u); fin_c0++; }
-                        else { mbar_wait(&bars->fin[1], fin_c1 & 1u); fin_c1++; }
-                    } else {
-                        if (t == 0) { mbar_wait(&bars->opnd[0][net], opnd_c0 & 1u); opnd_c0++; }
-                        else { mbar_wait(&bars->opnd[1][net], opnd_c1 & 1u); opnd_c1++; }
-                    }
-                    tc_fence_after();
-                    if (leader) {
-                        if (src < 2) {
-#pragma unroll 3
-                            for (int ks = 0; ks < nk; ++ks) umma_ts(acc, ta_hi + ks * 8, dhi + (uint64_t)(ks * 16), idesc, ks > 0 ? 1u : 0u);
-                            if (NPASS == 3) {
-#pragma unroll 3
-                                for (int ks = 0; ks < nk; ++ks) umma_ts(acc, ta_lo + ks * 8, dhi + (uint64_t)(ks * 16), idesc, 1u);
-#pragma unroll 3
-                                for (int ks = 0; ks < nk; ++ks) umma_ts(acc, ta_hi + ks * 8, dlo + (uint64_t)(ks * 16), idesc, 1u);
-                            }
-                        } else {
-#pragma unroll 5
-                            for (int ks = 0; ks < nk; ++ks) umma_bf16(acc, ahi + (uint64_t)(ks * 16), dhi + (uint64_t)(ks * 16), idesc, ks > 0 ? 1u : 0u);
-                            if (NPASS == 3) {
-#pragma unroll 5
-                                for (int ks = 0; ks < nk; ++ks) umma_bf16(acc, alo + (uint64_t)(ks * 16), dhi + (uint64_t)(ks * 16), idesc, 1u);
-#pragma unroll 5
-                                for (int ks = 0; ks < nk; ++ks) umma_bf16(acc, ahi + (uint64_t)(ks * 16), dlo + (uint64_t)(ks * 16), idesc, 1u);
-                            }
-                        }
-                        umma_commit(&bars->mma_done[t][net]);
-                        if (t == 1) umma_commit(&bars->empty[it & smask]);   // both tiles' MMAs done -> slot free
-                    }
-                    __syncwarp();
-                }
-            }
-            // consume the final `fin` phase of both tiles (the q-density epilogues) to stay in step with the groups
-            mbar_wait(&bars->fin[0], fin_c0 & 1u); fin_c0++;
-            mbar_wait(&bars->fin[1], fin_c1 & 1u); fin_c1++;
-            ring_it += (uint32_t)ts.nchunks;
-            continue;
-        }
-
-        // ===== compute groups: group g owns tile 2*pair + g; thread = (row, column part) =====
+// ===== compute groups: group g owns tile 2*pair + g; thread = (row, column part) =====
+// FOLD_D / FOLD_C: the density / coupling hidden layers of every step of this launch carry folded biases
+template <int NPASS, bool FOLD_D, bool FOLD_C>
+__device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, const RowArgs& a, const T3Dims& dm, long long pairs_per_step,
+                                        long long total_items, uint8_t* smem, uint32_t tmem_base) {
+    constexpr int NPARTS = 2;
+    const T3Smem m = t3_smem(smem, dm);
+    Bars3* bars = m.bars;
+    uint8_t* bias_ring = m.bias_ring;
+    const uint32_t h_stride = m.h_stride;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    X3 x;
+    x.lane = lane; x.g = (warp >> 3) & 1; x.part = (warp >> 2) & 1; x.row = (warp & 3) * 32 + lane;
+    x.tb = tmem_base + (uint32_t)x.g * kT3TileCols + ((uint32_t)((warp & 3) * 32) << 16);
+    x.bars = bars; x.slots = m.slots; x.slot_bytes = dm.slot_bytes; x.nslots_mask = m.smask; x.nslots_log2 = (uint32_t)dm.nslots_log2;
+    x.chunk_it = 0; x.mma_cnt0 = 0; x.mma_cnt1 = 0;
+    x.part_buf = m.part_all + x.g * 512;
+    x.bias_ring = smem_u32(bias_ring);
+    x.h_stride = h_stride;
+    x.h_base = smem_u32(m.hbuf) + (uint32_t)x.g * 4u * h_stride;
+    T3_ITEM_LOOP_BEGIN
+        const int C = ts.C, c = ts.c, Kin = ts.Kin, Ku = ts.Ku, Wd = ts.Wd, CPd = ts.CPd, Hc = ts.Hc;
         const int g = x.g;
         long long n = (pair * 2 + g) * 128 + x.row;
         const bool valid = n < a.N;
@@ -341,8 +365,9 @@ k_separate_tc3(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
                 for (int net = 0; net < 2; ++net) {
                     const uint32_t bias = x.bias_ring + (uint32_t)(net * 4 + ((x.chunk_it >> 1) & 3)) * kT3BiasEntry;
                     wait_mma3(x, net);
-                    epi_hidden3<NPASS, ACT_R, false, true>(x.tb + (net ? kT3Acc1 : kT3Acc0), x.h_base + (uint32_t)(net * 2) * h_stride,
-                                                           x.h_base + (uint32_t)(net * 2 + 1) * h_stride, bias, 0u, x.part, Wd, koff_d);
+                    const uint32_t acc = x.tb + (net ? kT3Acc1 : kT3Acc0);
+                    const uint32_t ohi = x.h_base + (uint32_t)(net * 2) * h_stride, olo = ohi + h_stride;
+                    epi_hidden3<NPASS, ACT_R, false, true, !FOLD_D>(acc, ohi, olo, bias, 0u, x.part, Wd, koff_d);
                     warp_arrive3(x, &bars->opnd[g][net]);
                     x.chunk_it++;
                 }
@@ -445,12 +470,14 @@ k_separate_tc3(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
                         const uint32_t acc = x.tb + (net ? kT3Acc1 : kT3Acc0);
                         const uint32_t ohi = x.h_base + (uint32_t)(net * 2) * h_stride, olo = ohi + h_stride;
                         if (!last) {
-                            if (net == 0) epi_hidden3<NPASS, ACT_T, false, true>(acc, ohi, olo, tail, 0u, x.part, Hc, koff_c);
-                            else epi_hidden3<NPASS, ACT_R, false, true>(acc, ohi, olo, tail, 0u, x.part, Hc, koff_c);
+                            if (net == 0) epi_hidden3<NPASS, ACT_T, false, true, !FOLD_C>(acc, ohi, olo, tail, 0u, x.part, Hc, koff_c);
+                            else epi_hidden3<NPASS, ACT_R, false, true, !FOLD_C>(acc, ohi, olo, tail, 0u, x.part, Hc, koff_c);
                             warp_arrive3(x, &bars->opnd[g][net]);
                         } else {
-                            if (net == 0) { ps = epi_hidden3<NPASS, ACT_T, true, false>(acc, ohi, olo, tail, tail + Hc * 4, x.part, Hc, koff_c); bs = lds32(tail + Hc * 8); }
-                            else { pt_ = epi_hidden3<NPASS, ACT_R, true, false>(acc, ohi, olo, tail, tail + Hc * 4, x.part, Hc, koff_c); bt = lds32(tail + Hc * 8); }
+                            float pd;
+                            if (net == 0) pd = epi_hidden3<NPASS, ACT_T, true, false, !FOLD_C>(acc, ohi, olo, tail, tail + Hc * 4, x.part, Hc, koff_c);
+                            else pd = epi_hidden3<NPASS, ACT_R, true, false, !FOLD_C>(acc, ohi, olo, tail, tail + Hc * 4, x.part, Hc, koff_c);
+                            if (net == 0) { ps = pd; bs = lds32(tail + Hc * 8); } else { pt_ = pd; bt = lds32(tail + Hc * 8); }
                         }
                     }
                 }
@@ -489,7 +516,56 @@ k_separate_tc3(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
             const float lp = normal_lp2(z0, z1, prev0, prev1, ts.std[0], ts.std[1]) + lacc;
             a.out[ag * a.out_sa + rem * a.out_sp + (long long)step * a.out_st] = lp;
         }
+    T3_ITEM_LOOP_END
+}
+
+}  // namespace t3
+
+template <int NPASS, bool FOLD_D, bool FOLD_C>
+__global__ void __launch_bounds__(kT3Threads, 1)
+k_separate_tc3(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img, const __grid_constant__ RowArgs a,
+               const __grid_constant__ T3Dims dm, long long pairs_per_step, long long total_items) {
+    using namespace tc;
+    using namespace t2;
+    using namespace t3;
+    extern __shared__ __align__(128) uint8_t smem_t3[];
+    uint8_t* smem = smem_t3;
+    Bars3* bars = reinterpret_cast<Bars3*>(smem);
+    static_assert(sizeof(Bars3) <= 240, "barrier block");
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + 240);
+    static_assert(sizeof(T2Step) <= 1792, "T2Step must fit the header");
+    const uint32_t nslots = 1u << dm.nslots_log2;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) {
+        for (uint32_t s = 0; s < nslots; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(&bars->mma_done[t][0], 1);
+            mbar_init(&bars->mma_done[t][1], 1);
+            mbar_init(&bars->opnd[t][0], 8);
+            mbar_init(&bars->opnd[t][1], 8);
+            mbar_init(&bars->fin[t], 8);
+        }
+        mbar_fence_init();
     }
+    {   // constant A operand of the bias fold: row r = [1, 1, 1, 0 x 13] in the canonical K-major layout (Kp = 16)
+        uint32_t* ones = reinterpret_cast<uint32_t*>(smem + kT3OnesOff);
+        for (int i = tid; i < 1024; i += kT3Threads) {            // 128 rows x 2 core columns x 16 B = 4 KB
+            const int w = i & 3, kc = (i >> 5) & 1;               // word inside the 16-byte row piece, core column (k / 8)
+            ones[i] = kc == 0 ? (w == 0 ? 0x3C003C00u : (w == 1 ? 0x00003C00u : 0u)) : 0u;
+        }
+        fence_async_smem();
+    }
+    if (warp == 16) tmem_alloc(tslot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tslot);
+
+    // three roles (inlined: separate noinline role functions measured 3 ms slower)
+    if (warp < 16) t3_compute<NPASS, FOLD_D, FOLD_C>(steps, a, dm, pairs_per_step, total_items, smem, tmem_base);
+    else if (warp == 16) t3_producer(steps, img, dm, pairs_per_step, total_items, smem);
+    else t3_issuer<NPASS>(steps, dm, pairs_per_step, total_items, smem, tmem_base, warp - 17);
 
     tc_fence_before();
     __syncthreads();
@@ -508,10 +584,12 @@ inline int tc3_launch_separate(const T2Dims& dm2, const std::vector<T2Step>& hst
     int lo = 0;
     while (lo < T) {
         // group consecutive steps with the same operand-width class
-        auto wclass = [&](int s) { const int w = hsteps[s].Wd > hsteps[s].Hc ? hsteps[s].Wd : hsteps[s].Hc; return w <= 64 ? 64 : 80; };
+        // (the class also fixes which hidden layers carry folded biases: tc2_pack folds widths <= kFoldMaxN = 64)
+        auto wclass = [&](int s) { const int w = hsteps[s].Wd > hsteps[s].Hc ? hsteps[s].Wd : hsteps[s].Hc; return (w <= 64 ? 64 : 80) + (hsteps[s].Wd <= kFoldMaxN ? 1 : 0); };
         int hi = lo;
-        const int wc = wclass(lo);
-        while (hi + 1 < T && wclass(hi + 1) == wc) ++hi;
+        const int wc = wclass(lo) & ~1;
+        const bool fold_d = hsteps[lo].Wd <= kFoldMaxN, fold_c = hsteps[lo].Hc <= kFoldMaxN;
+        while (hi + 1 < T && wclass(hi + 1) == wclass(lo)) ++hi;
         int slot = 0;
         for (int s = lo; s <= hi; ++s)
             for (int ci = 0; ci < hsteps[s].nchunks; ++ci) slot = hsteps[s].chunk_bytes[ci] > slot ? hsteps[s].chunk_bytes[ci] : slot;
@@ -529,11 +607,18 @@ inline int tc3_launch_separate(const T2Dims& dm2, const std::vector<T2Step>& hst
             lo = hi + 1;
             continue;
         }
-        cudaError_t e = cudaFuncSetAttribute(k_separate_tc3<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { *msg = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return 1; }
         const long long items = pairs * (hi - lo + 1);
         const int grid = (int)(items < num_sms ? items : num_sms);
-        k_separate_tc3<NPASS><<<grid, kT3Threads, smem, stream>>>(d_steps, d_img, a, dm, pairs, items);
+        cudaError_t e = cudaSuccess;
+        auto go = [&](auto kern) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) kern<<<grid, kT3Threads, smem, stream>>>(d_steps, d_img, a, dm, pairs, items);
+        };
+        if (fold_d && fold_c) go(k_separate_tc3<NPASS, true, true>);
+        else if (fold_c) go(k_separate_tc3<NPASS, false, true>);
+        else if (fold_d) go(k_separate_tc3<NPASS, true, false>);
+        else go(k_separate_tc3<NPASS, false, false>);
+        if (e != cudaSuccess) { *msg = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return 1; }
         (*launches)++;
         e = cudaGetLastError();
         if (e != cudaSuccess) { *msg = std::string("k_separate_tc3 launch: ") + cudaGetErrorString(e); return 1; }
