@@ -100,6 +100,38 @@ __device__ __noinline__ float epi_hidden3(uint32_t acc, uint32_t ohi, uint32_t o
     return dot;
 }
 
+// Epilogue of a layer that is exactly 16 * NB columns wide: this thread's NB chunks are processed in unguarded pairs,
+// so the compiler interleaves the 16 independent value chains of a pair (the guarded loop above keeps every chunk in
+// its own basic block); all NB at once measured slower than pairs.
+template <int NPASS, int ACT, bool DOT, bool WRITE, bool BIAS, int NB>
+__device__ __noinline__ float epi_hidden3_nb(uint32_t acc, uint32_t ohi, uint32_t olo, uint32_t bias, uint32_t wlast, int part, uint32_t koff) {
+    float dot = 0.0f;
+    const int c0 = part * 8;
+#pragma unroll
+    for (int j = 0; j < NB; j += 2) {
+        const int ca = c0 + 16 * j, cb = ca + 16;
+        float v0[8], v1[8];
+        tmem_ld8(acc + (uint32_t)ca, v0);
+        if (j + 1 < NB) tmem_ld8(acc + (uint32_t)cb, v1);
+        float4 b00 = make_float4(0.f, 0.f, 0.f, 0.f), b01 = b00, b10 = b00, b11 = b00;
+        if (BIAS) {
+            b00 = lds128(bias + (uint32_t)ca * 4); b01 = lds128(bias + (uint32_t)ca * 4 + 16);
+            if (j + 1 < NB) { b10 = lds128(bias + (uint32_t)cb * 4); b11 = lds128(bias + (uint32_t)cb * 4 + 16); }
+        }
+        tmem_wait_ld();
+        epi_chunk3<NPASS, ACT, DOT, WRITE, BIAS>(v0, ca, b00, b01, wlast, ohi, olo, koff, dot);
+        if (j + 1 < NB) epi_chunk3<NPASS, ACT, DOT, WRITE, BIAS>(v1, cb, b10, b11, wlast, ohi, olo, koff, dot);
+    }
+    return dot;
+}
+template <int NPASS, int ACT, bool DOT, bool WRITE, bool BIAS>
+__device__ __forceinline__ float epi_layer3(uint32_t acc, uint32_t ohi, uint32_t olo, uint32_t bias, uint32_t wlast, int part, int W, uint32_t koff) {
+    if (W == 64) return epi_hidden3_nb<NPASS, ACT, DOT, WRITE, BIAS, 4>(acc, ohi, olo, bias, wlast, part, koff);
+    if (W == 48) return epi_hidden3_nb<NPASS, ACT, DOT, WRITE, BIAS, 3>(acc, ohi, olo, bias, wlast, part, koff);
+    if (W == 80) return epi_hidden3_nb<NPASS, ACT, DOT, WRITE, BIAS, 5>(acc, ohi, olo, bias, wlast, part, koff);
+    return epi_hidden3<NPASS, ACT, DOT, WRITE, BIAS>(acc, ohi, olo, bias, wlast, part, W, koff);
+}
+
 // per-thread view of its group (tile)
 struct X3 {
     int row, part, lane, g;
@@ -367,7 +399,7 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
                     wait_mma3(x, net);
                     const uint32_t acc = x.tb + (net ? kT3Acc1 : kT3Acc0);
                     const uint32_t ohi = x.h_base + (uint32_t)(net * 2) * h_stride, olo = ohi + h_stride;
-                    epi_hidden3<NPASS, ACT_R, false, true, !FOLD_D>(acc, ohi, olo, bias, 0u, x.part, Wd, koff_d);
+                    epi_layer3<NPASS, ACT_R, false, true, !FOLD_D>(acc, ohi, olo, bias, 0u, x.part, Wd, koff_d);
                     warp_arrive3(x, &bars->opnd[g][net]);
                     x.chunk_it++;
                 }
@@ -470,13 +502,13 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
                         const uint32_t acc = x.tb + (net ? kT3Acc1 : kT3Acc0);
                         const uint32_t ohi = x.h_base + (uint32_t)(net * 2) * h_stride, olo = ohi + h_stride;
                         if (!last) {
-                            if (net == 0) epi_hidden3<NPASS, ACT_T, false, true, !FOLD_C>(acc, ohi, olo, tail, 0u, x.part, Hc, koff_c);
-                            else epi_hidden3<NPASS, ACT_R, false, true, !FOLD_C>(acc, ohi, olo, tail, 0u, x.part, Hc, koff_c);
+                            if (net == 0) epi_layer3<NPASS, ACT_T, false, true, !FOLD_C>(acc, ohi, olo, tail, 0u, x.part, Hc, koff_c);
+                            else epi_layer3<NPASS, ACT_R, false, true, !FOLD_C>(acc, ohi, olo, tail, 0u, x.part, Hc, koff_c);
                             warp_arrive3(x, &bars->opnd[g][net]);
                         } else {
                             float pd;
-                            if (net == 0) pd = epi_hidden3<NPASS, ACT_T, true, false, !FOLD_C>(acc, ohi, olo, tail, tail + Hc * 4, x.part, Hc, koff_c);
-                            else pd = epi_hidden3<NPASS, ACT_R, true, false, !FOLD_C>(acc, ohi, olo, tail, tail + Hc * 4, x.part, Hc, koff_c);
+                            if (net == 0) pd = epi_layer3<NPASS, ACT_T, true, false, !FOLD_C>(acc, ohi, olo, tail, tail + Hc * 4, x.part, Hc, koff_c);
+                            else pd = epi_layer3<NPASS, ACT_R, true, false, !FOLD_C>(acc, ohi, olo, tail, tail + Hc * 4, x.part, Hc, koff_c);
                             if (net == 0) { ps = pd; bs = lds32(tail + Hc * 8); } else { pt_ = pd; bt = lds32(tail + Hc * 8); }
                         }
                     }
