@@ -337,9 +337,14 @@ int launch_density(fc_handle* h, RowArgs a, Mode mode, int precision, cudaStream
         return 0;
     }
     if (precision == FC_PREC_F16X3 || precision == FC_PREC_F16) {
-        if (mode != MODE_SEPARATE) return fail(h, "the tensor-core path implements the per-step density only");
         std::string msg;
         const int i = precision == FC_PREC_F16X3 ? 0 : 1;
+        if (mode == MODE_SEQUENTIAL) {      // chain mode runs on the two-tile kernel only
+            int rcs = i == 0 ? fc::tc3_launch_sequential<3>(h->t2dims[0], h->t2steps_host[0], h->d_t2steps[0], h->d_t2img[0], a, h->num_sms, h->smem_optin, stream, &h->launches, &msg)
+                             : fc::tc3_launch_sequential<1>(h->t2dims[1], h->t2steps_host[1], h->d_t2steps[1], h->d_t2img[1], a, h->num_sms, h->smem_optin, stream, &h->launches, &msg);
+            if (rcs) return fail(h, "%s", msg.c_str());
+            return 0;
+        }
         if (h->tc_kernel == 3) {
             int rc3 = i == 0 ? fc::tc3_launch_separate<3>(h->t2dims[0], h->t2steps_host[0], h->d_t2steps[0], h->d_t2img[0], a, h->num_sms, h->smem_optin, stream, &h->launches, &msg)
                              : fc::tc3_launch_separate<1>(h->t2dims[1], h->t2steps_host[1], h->d_t2steps[1], h->d_t2img[1], a, h->num_sms, h->smem_optin, stream, &h->launches, &msg);

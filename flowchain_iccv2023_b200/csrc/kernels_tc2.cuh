@@ -35,7 +35,7 @@ constexpr uint32_t kT2H1Hi = 384, kT2H1Lo = 432;         // hidden operand of ne
 
 struct T2Step {
     int32_t C, c, Kin, Ku, Wd, CPd, Hc;
-    int32_t n_blocks, n_hidden, nchunks, eps_off, pad0;
+    int32_t n_blocks, n_hidden, nchunks, eps_off, seq_eps_off;   // noise-tape offsets: per-step / chain ("sequential") layout
     int32_t chunk_off[kT2MaxChunks];
     int32_t chunk_bytes[kT2MaxChunks];
     int32_t masked_dim[kMaxBlocks];
@@ -83,7 +83,7 @@ inline void tc2_pack(const fc_model_desc& d, const std::vector<StepPlan>& plans,
         const TcStepSrc& s = src[i];
         const int C = sp.C, c = sp.c;
         ts.C = C; ts.c = c; ts.Kin = pad16i(c); ts.Ku = pad16i(C + 2); ts.Wd = pad16i(2 * c); ts.CPd = pad16i(C); ts.Hc = H;
-        ts.n_blocks = sp.n_blocks; ts.n_hidden = sp.n_hidden; ts.eps_off = sp.eps_off;
+        ts.n_blocks = sp.n_blocks; ts.n_hidden = sp.n_hidden; ts.eps_off = sp.eps_off; ts.seq_eps_off = sp.seq_eps_off;
         for (int b = 0; b < sp.n_blocks; ++b) {
             ts.masked_dim[b] = sp.masked_dim[b];
             ts.bn_scale[b][0] = sp.bn_scale[b][0]; ts.bn_scale[b][1] = sp.bn_scale[b][1];

@@ -29,7 +29,10 @@ struct T3Dims {
     int32_t nslots_log2;     // ring depth (1 -> 2 slots, 2 -> 4 slots)
     int32_t Wmax;            // widest hidden operand of the launched steps (64 or 80): shared-memory operand stride
     int32_t T, C0;
-    int32_t step_lo, step_hi;   // inclusive range of steps this launch covers
+    int32_t step_lo, step_hi;   // inclusive range of steps (per-step mode) / result indices (chain mode) this launch covers
+    int32_t seq;                // 1: chain mode (flow.log_prob_sequential): item (tiles, j) applies net[j], ..., net[klo]
+    int32_t klo, jlo;           // chain mode: lowest chain step applied, first result index written
+    int32_t no_fold;            // 1: ignore the chunks' bias tiles (launches whose steps mix folded and plain widths)
 };
 
 namespace t3 {
@@ -204,15 +207,21 @@ __device__ __forceinline__ void t3_load_step(const T2Step* steps, int step, T2St
     for (int i = tid; i < nw; i += kT3Threads) d[i] = __ldg(s + i);
     __syncthreads();
 }
-#define T3_ITEM_LOOP_BEGIN                                                                          \
+// Item = (tile pair, jstep).  Per-step mode: one step (= jstep).  Chain mode: steps jstep, jstep-1, ..., klo with the
+// point carried in registers.  Every role runs exactly these loops so that the step-table reloads line up.
+#define T3_ITEM_BEGIN                                                                               \
     int cur_step = -1;                                                                              \
     for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {                      \
-        const int step = dm.step_hi - (int)(item / pairs_per_step); /* heavy (late) steps first */  \
+        const int jstep = dm.step_hi - (int)(item / pairs_per_step); /* heavy (late) first */       \
         const long long pair = item % pairs_per_step;                                               \
-        (void)pair;                                                                                 \
-        if (step != cur_step) { t3_load_step(steps, step, m.cur, (int)threadIdx.x); cur_step = step; } \
-        const T2Step& ts = *m.cur;
-#define T3_ITEM_LOOP_END }
+        const int klast = dm.seq ? dm.klo : jstep;                                                  \
+        (void)pair;
+#define T3_STEP_BEGIN                                                                               \
+        for (int step = jstep; step >= klast; --step) {                                             \
+            if (step != cur_step) { t3_load_step(steps, step, m.cur, (int)threadIdx.x); cur_step = step; } \
+            const T2Step& ts = *m.cur;
+#define T3_STEP_END }
+#define T3_ITEM_END }
 
 // ===== weight producer (one warp): streams the step's chunks through the ring =====
 __device__ __forceinline__ void t3_producer(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img, const T3Dims& dm,
@@ -223,7 +232,8 @@ __device__ __forceinline__ void t3_producer(const T2Step* __restrict__ steps, co
     const uint32_t smask = m.smask;
     const int lane = threadIdx.x & 31;
     uint32_t ring_it = 0;
-    T3_ITEM_LOOP_BEGIN
+    T3_ITEM_BEGIN
+    T3_STEP_BEGIN
         for (int ci = 0; ci < ts.nchunks; ++ci, ++ring_it) {
             if (lane == 0) {
                 const uint32_t slot = ring_it & smask;
@@ -233,7 +243,8 @@ __device__ __forceinline__ void t3_producer(const T2Step* __restrict__ steps, co
             }
             __syncwarp();
         }
-    T3_ITEM_LOOP_END
+    T3_STEP_END
+    T3_ITEM_END
 }
 
 // ===== MMA issuers, one warp per net; every net-layer is issued for tile 0 then tile 1 from the same weight chunk.
@@ -248,20 +259,21 @@ __device__ __forceinline__ void t3_issuer(const T2Step* __restrict__ steps, cons
     const int lane = threadIdx.x & 31;
     uint32_t ring_it = 0;
     uint32_t opnd_c0 = 0, opnd_c1 = 0, fin_c0 = 0, fin_c1 = 0;    // per-tile phase counters
-    T3_ITEM_LOOP_BEGIN
+    T3_ITEM_BEGIN
+    T3_STEP_BEGIN
         const uint32_t base = ring_it;
 #pragma unroll 1
         for (int ci = net; ci < ts.nchunks; ci += 2) {
             const uint32_t it = base + (uint32_t)ci;
             mbar_wait(&bars->full[it & smask], (it >> dm.nslots_log2) & 1u);
             const int w = ts.job_wait[ci], src = ts.job_src[ci], Kp = ts.job_kp[ci], N = ts.job_n[ci];
-            const bool fold = ts.job_fold[ci] != 0;
+            const bool has_bias_tile = ts.job_fold[ci] != 0, fold = has_bias_tile && !dm.no_fold;
             const uint8_t* chunk = slots + (size_t)(it & smask) * dm.slot_bytes;
             const uint32_t b_hi = smem_u32(chunk);
             {   // the fp32 tail (biases, last-row vector) moves to the bias ring so that the weight slot can be handed
                 // back as soon as the MMAs that read it complete (tcgen05.commit -> empty), not after the epilogue
                 const int tiles_b = (NPASS == 3 ? 2 : 1) * N * Kp * 2;
-                const int n16 = (ts.chunk_bytes[ci] - tiles_b - (fold ? N * 32 : 0)) >> 4;
+                const int n16 = (ts.chunk_bytes[ci] - tiles_b - (has_bias_tile ? N * 32 : 0)) >> 4;
                 const float4* srcp = reinterpret_cast<const float4*>(chunk + tiles_b);
                 float4* dstp = reinterpret_cast<float4*>(bias_ring + (size_t)(net * 4 + ((it >> 1) & 3)) * kT3BiasEntry);
                 for (int q = lane; q < n16; q += 32) dstp[q] = srcp[q];
@@ -323,7 +335,8 @@ __device__ __forceinline__ void t3_issuer(const T2Step* __restrict__ steps, cons
         mbar_wait(&bars->fin[0], fin_c0 & 1u); fin_c0++;
         mbar_wait(&bars->fin[1], fin_c1 & 1u); fin_c1++;
         ring_it += (uint32_t)ts.nchunks;
-    T3_ITEM_LOOP_END
+    T3_STEP_END
+    T3_ITEM_END
 }
 
 // ===== compute groups: group g owns tile 2*pair + g; thread = (row, column part) =====
@@ -346,8 +359,7 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
     x.bias_ring = smem_u32(bias_ring);
     x.h_stride = h_stride;
     x.h_base = smem_u32(m.hbuf) + (uint32_t)x.g * 4u * h_stride;
-    T3_ITEM_LOOP_BEGIN
-        const int C = ts.C, c = ts.c, Kin = ts.Kin, Ku = ts.Ku, Wd = ts.Wd, CPd = ts.CPd, Hc = ts.Hc;
+    T3_ITEM_BEGIN
         const int g = x.g;
         long long n = (pair * 2 + g) * 128 + x.row;
         const bool valid = n < a.N;
@@ -355,17 +367,20 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
         const long long ag = n / a.PPA, rem = n % a.PPA, pt = rem / a.K;
         float z0, z1, prev0, prev1, lacc = 0.0f;
         {
-            const float* xp = src_at(a.x, ag, pt, step);
+            const float* xp = src_at(a.x, ag, pt, jstep);
             z0 = __ldg(xp); z1 = __ldg(xp + 1);
-            const float* pp = step == 0 ? src_at(a.base, ag, pt, 0) : src_at(a.prefix, ag, pt, step - 1);
+            // base mean: per-step mode = previous trajectory point; chain mode = base_pos (fastpredNF.py:454-458)
+            const float* pp = (dm.seq || jstep == 0) ? src_at(a.base, ag, pt, 0) : src_at(a.prefix, ag, pt, jstep - 1);
             prev0 = __ldg(pp); prev1 = __ldg(pp + 1);
         }
+    T3_STEP_BEGIN
+        const int C = ts.C, c = ts.c, Kin = ts.Kin, Ku = ts.Ku, Wd = ts.Wd, CPd = ts.CPd, Hc = ts.Hc;
         // byte offset of this row inside a canonical [128 x W] operand tile, for the two hidden widths of the step
         const uint32_t koff_d = (uint32_t)((x.row >> 3) * (Wd >> 3) * 128 + (x.row & 7) * 16);
         const uint32_t koff_c = (uint32_t)((x.row >> 3) * (Hc >> 3) * 128 + (x.row & 7) * 16);
         // ---- input operand [z (2), cond (C0), prefix (2*step), 0...] ----
         {
-            const float* cp = src_at(a.cond, ag, pt, step) - 2;
+            const float* cp = src_at(a.cond, ag, pt, jstep) - 2;     // chain mode: cond[:, j] for every chain step
             const float* pf = src_at(a.prefix, ag, pt, 0);
             const long long pst = a.prefix.st;
             const int c0e = 2 + dm.C0;
@@ -425,11 +440,11 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
                         tmem_ld8(x.tb + kT3Acc0 + (uint32_t)d0, mu);
                         tmem_ld8(x.tb + kT3Acc1 + (uint32_t)d0, ls);
                         if (a.eps != nullptr) {
-                            const float* ep = a.eps + n * a.eps_rs + ts.eps_off + d0;
+                            const float* ep = a.eps + n * a.eps_rs + (dm.seq ? ts.seq_eps_off + (jstep - step) * C : ts.eps_off) + d0;
 #pragma unroll
                             for (int i = 0; i < 8; ++i) if (d0 + i < C) e[i] = __ldg(ep + i);
                         } else {
-                            const Normal8 gn = philox_normal8(a.seed, n, (unsigned)step, (unsigned)(d0 >> 2));
+                            const Normal8 gn = philox_normal8(a.seed, n, dm.seq ? (unsigned)(step * 64 + jstep + 4096) : (unsigned)step, (unsigned)(d0 >> 2));
                             e[0] = gn.a.x; e[1] = gn.a.y; e[2] = gn.a.z; e[3] = gn.a.w; e[4] = gn.b.x; e[5] = gn.b.y; e[6] = gn.b.z; e[7] = gn.b.w;
                         }
                         tmem_wait_ld();
@@ -544,11 +559,17 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
                 warp_arrive3(x, &bars->fin[g]);
             }
         }
+    T3_STEP_END
         if (valid && x.part == 0) {
-            const float lp = normal_lp2(z0, z1, prev0, prev1, ts.std[0], ts.std[1]) + lacc;
-            a.out[ag * a.out_sa + rem * a.out_sp + (long long)step * a.out_st] = lp;
+            if (!dm.seq) {
+                const float lp = normal_lp2(z0, z1, prev0, prev1, m.cur->std[0], m.cur->std[1]) + lacc;
+                a.out[ag * a.out_sa + rem * a.out_sp + (long long)jstep * a.out_st] = lp;
+            } else {      // base = Normal(base_pos, std[0]); ldj = mean over the chain steps of this result index
+                const float lp = normal_lp2(z0, z1, prev0, prev1, __ldg(&steps[0].std[0]), __ldg(&steps[0].std[1])) + lacc / (float)(jstep - dm.jlo + 1);
+                a.out[ag * a.out_sa + rem * a.out_sp + (long long)(jstep - dm.jlo) * a.out_st] = lp;
+            }
         }
-    T3_ITEM_LOOP_END
+    T3_ITEM_END
 }
 
 }  // namespace t3
@@ -656,6 +677,41 @@ inline int tc3_launch_separate(const T2Dims& dm2, const std::vector<T2Step>& hst
         if (e != cudaSuccess) { *msg = std::string("k_separate_tc3 launch: ") + cudaGetErrorString(e); return 1; }
         lo = hi + 1;
     }
+    return 0;
+}
+
+// Chain mode (flow.log_prob_sequential, fastpredNF.py:548-569): one launch, item = (tile pair, result index j) walks
+// net[j] ... net[klo]; the steps of an item mix operand widths, so the operand stride is the widest one and the bias
+// tiles are ignored (no_fold).
+template <int NPASS>
+inline int tc3_launch_sequential(const T2Dims& dm2, const std::vector<T2Step>& hsteps, const T2Step* d_steps, const unsigned char* d_img,
+                                 const RowArgs& a, int num_sms, int smem_optin, cudaStream_t stream, uint64_t* launches, std::string* msg) {
+    if (!dm2.supported || d_img == nullptr) { *msg = "the tensor-core path does not support this model shape; use FC_PREC_FP32"; return 1; }
+    const int T = dm2.T;
+    const long long tiles = (a.N + 127) / 128, pairs = (tiles + 1) / 2;
+    int wc = 64, slot = 0;
+    for (int s = 0; s < T; ++s) {
+        const int w = hsteps[s].Wd > hsteps[s].Hc ? hsteps[s].Wd : hsteps[s].Hc;
+        wc = w > wc ? w : wc;
+        for (int ci = 0; ci < hsteps[s].nchunks; ++ci) slot = hsteps[s].chunk_bytes[ci] > slot ? hsteps[s].chunk_bytes[ci] : slot;
+    }
+    slot = (slot + 127) / 128 * 128;
+    T3Dims dm{};
+    dm.slot_bytes = slot; dm.Wmax = wc; dm.T = T; dm.C0 = dm2.C0; dm.step_lo = a.seq_jlo; dm.step_hi = T - 1;
+    dm.seq = 1; dm.klo = a.seq_klo; dm.jlo = a.seq_jlo; dm.no_fold = 1;
+    const size_t fixed = (size_t)kT3Header + (size_t)8 * 128 * wc * 2;
+    dm.nslots_log2 = (fixed + (size_t)4 * slot <= (size_t)smem_optin) ? 2 : 1;
+    const size_t smem = fixed + ((size_t)1 << dm.nslots_log2) * slot;
+    if (wc > 80 || smem > (size_t)smem_optin) { *msg = "the tensor-core chain kernel does not fit this model shape; use FC_PREC_FP32"; return 1; }
+    auto kern = k_separate_tc3<NPASS, false, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { *msg = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return 1; }
+    const long long items = pairs * (T - a.seq_jlo);
+    const int grid = (int)(items < num_sms ? items : num_sms);
+    kern<<<grid, kT3Threads, smem, stream>>>(d_steps, d_img, a, dm, pairs, items);
+    (*launches)++;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { *msg = std::string("k_separate_tc3 (chain) launch: ") + cudaGetErrorString(e); return 1; }
     return 0;
 }
 
