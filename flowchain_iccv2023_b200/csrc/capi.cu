@@ -483,7 +483,8 @@ extern "C" int fc_sample_with_log_prob(fc_handle* h, const float* base_pos, cons
     if (B < 0 || S < 0) return fail(h, "negative size");
     if (B == 0 || S == 0) return 0;
     if (!base_pos || !cond || !seq || !log_prob || !ldjs || !base_lp) return fail(h, "null tensor pointer");
-    if (precision != FC_PREC_FP32) return fail(h, "the sampler runs on the fp32 path only");
+    if (precision != FC_PREC_FP32 && precision != FC_PREC_F16X3 && precision != FC_PREC_F16)
+        return fail(h, "the sampler runs with FC_PREC_FP32, FC_PREC_F16X3 or FC_PREC_F16");
     const int T = h->desc.pred_len, C0 = h->desc.cond_size;
     RowArgs a{};
     a.cond = Src{cond, (long long)T * C0, 0, C0};
@@ -492,6 +493,14 @@ extern "C" int fc_sample_with_log_prob(fc_handle* h, const float* base_pos, cons
     a.eps = eps; a.eps_rs = h->E; a.z0 = z0; a.seed = seed;
     a.N = B * S; a.PPA = S; a.K = 1;
     SampleOut o{seq, log_prob, ldjs, base_lp};
+    if (precision != FC_PREC_FP32) {     // tensor-core sampler: the two-tile kernel run in the inverse direction
+        std::string msg;
+        const int i = precision == FC_PREC_F16X3 ? 0 : 1;
+        int rc = i == 0 ? fc::tc3_launch_sample<3>(h->t2dims[0], h->t2steps_host[0], h->d_t2steps[0], h->d_t2img[0], a, o, h->num_sms, h->smem_optin, (cudaStream_t)stream, &h->launches, &msg)
+                        : fc::tc3_launch_sample<1>(h->t2dims[1], h->t2steps_host[1], h->d_t2steps[1], h->d_t2img[1], a, o, h->num_sms, h->smem_optin, (cudaStream_t)stream, &h->launches, &msg);
+        if (rc) return fail(h, "%s", msg.c_str());
+        return 0;
+    }
     const bool wide = (int)smem_bytes_fp32(h->dims, 64, true) > h->smem_optin;
     const int R = wide ? 32 : 64;
     const long long tiles = (a.N + R - 1) / R;

@@ -40,6 +40,7 @@ struct T2Step {
     int32_t chunk_bytes[kT2MaxChunks];
     int32_t masked_dim[kMaxBlocks];
     float bn_scale[kMaxBlocks][2], bn_shift[kMaxBlocks][2], bn_ldj[kMaxBlocks];
+    float bn_iscale[kMaxBlocks][2], bn_ishift[kMaxBlocks][2];     // BatchNorm.inverse: x = iscale * y + ishift (sampler)
     float std[2];
     // MMA-issuer schedule, one entry per chunk (= net-layer), executed in order:
     //   wait on barrier `wait` (0 none, 1 opnd[0], 2 opnd[1], 3 fin) -> issue the MMAs -> hand back `rel` older chunks
@@ -89,6 +90,8 @@ inline void tc2_pack(const fc_model_desc& d, const std::vector<StepPlan>& plans,
             ts.bn_scale[b][0] = sp.bn_scale[b][0]; ts.bn_scale[b][1] = sp.bn_scale[b][1];
             ts.bn_shift[b][0] = sp.bn_shift[b][0]; ts.bn_shift[b][1] = sp.bn_shift[b][1];
             ts.bn_ldj[b] = sp.bn_ldj[b];
+            ts.bn_iscale[b][0] = sp.bn_iscale[b][0]; ts.bn_iscale[b][1] = sp.bn_iscale[b][1];
+            ts.bn_ishift[b][0] = sp.bn_ishift[b][0]; ts.bn_ishift[b][1] = sp.bn_ishift[b][1];
         }
         ts.std[0] = sp.std[0]; ts.std[1] = sp.std[1];
         int nch = 0;

@@ -30,7 +30,8 @@ struct T3Dims {
     int32_t Wmax;            // widest hidden operand of the launched steps (64 or 80): shared-memory operand stride
     int32_t T, C0;
     int32_t step_lo, step_hi;   // inclusive range of steps (per-step mode) / result indices (chain mode) this launch covers
-    int32_t seq;                // 1: chain mode (flow.log_prob_sequential): item (tiles, j) applies net[j], ..., net[klo]
+    int32_t seq;                // 1: chain mode (flow.log_prob_sequential): item (tiles, j) applies net[j], ..., net[klo];
+                                // 2: sampler (flow.sample_with_log_prob): item = tiles, inverse steps 0 .. T-1
     int32_t klo, jlo;           // chain mode: lowest chain step applied, first result index written
     int32_t no_fold;            // 1: ignore the chunks' bias tiles (launches whose steps mix folded and plain widths)
 };
@@ -209,19 +210,30 @@ __device__ __forceinline__ void t3_load_step(const T2Step* steps, int step, T2St
 }
 // Item = (tile pair, jstep).  Per-step mode: one step (= jstep).  Chain mode: steps jstep, jstep-1, ..., klo with the
 // point carried in registers.  Every role runs exactly these loops so that the step-table reloads line up.
-#define T3_ITEM_BEGIN                                                                               \
+#define T3_ITEM_BEGIN(SEQ)                                                                            \
     int cur_step = -1;                                                                              \
     for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {                      \
         const int jstep = dm.step_hi - (int)(item / pairs_per_step); /* heavy (late) first */       \
         const long long pair = item % pairs_per_step;                                               \
-        const int klast = dm.seq ? dm.klo : jstep;                                                  \
+        const int nsteps = (SEQ) == 0 ? 1 : ((SEQ) == 1 ? jstep - dm.klo + 1 : dm.T);           \
         (void)pair;
-#define T3_STEP_BEGIN                                                                               \
-        for (int step = jstep; step >= klast; --step) {                                             \
+#define T3_STEP_BEGIN(SEQ)                                                                            \
+        for (int si = 0; si < nsteps; ++si) {                                                       \
+            const int step = (SEQ) == 2 ? si : jstep - si;                                       \
             if (step != cur_step) { t3_load_step(steps, step, m.cur, (int)threadIdx.x); cur_step = step; } \
             const T2Step& ts = *m.cur;
 #define T3_STEP_END }
 #define T3_ITEM_END }
+
+// The image holds a step's chunks in forward order [density r][blocks 0 .. n-1][density q]; the sampler runs the inverse
+// [density q][blocks n-1 .. 0][density r] with an identical job table (same shapes), so only the chunk index is mapped.
+__device__ __forceinline__ int t3_chunk_of_job(const T2Step& ts, int ci, bool inverse) {
+    if (!inverse) return ci;
+    const int L2 = 2 * (ts.n_hidden + 1), nb6 = 6 + ts.n_blocks * L2;
+    if (ci < 6) return nb6 + ci;
+    if (ci < nb6) { const int bi = (ci - 6) / L2; return 6 + (ts.n_blocks - 1 - bi) * L2 + (ci - 6 - bi * L2); }
+    return ci - nb6;
+}
 
 // ===== weight producer (one warp): streams the step's chunks through the ring =====
 __device__ __forceinline__ void t3_producer(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img, const T3Dims& dm,
@@ -232,14 +244,15 @@ __device__ __forceinline__ void t3_producer(const T2Step* __restrict__ steps, co
     const uint32_t smask = m.smask;
     const int lane = threadIdx.x & 31;
     uint32_t ring_it = 0;
-    T3_ITEM_BEGIN
-    T3_STEP_BEGIN
+    T3_ITEM_BEGIN(dm.seq)
+    T3_STEP_BEGIN(dm.seq)
         for (int ci = 0; ci < ts.nchunks; ++ci, ++ring_it) {
             if (lane == 0) {
                 const uint32_t slot = ring_it & smask;
                 mbar_wait(&bars->empty[slot], ((ring_it >> dm.nslots_log2) & 1u) ^ 1u);
-                mbar_expect_tx(&bars->full[slot], (uint32_t)ts.chunk_bytes[ci]);
-                bulk_load(slots + (size_t)slot * dm.slot_bytes, img + ts.chunk_off[ci], (uint32_t)ts.chunk_bytes[ci], &bars->full[slot]);
+                const int pc = t3_chunk_of_job(ts, ci, dm.seq == 2);
+                mbar_expect_tx(&bars->full[slot], (uint32_t)ts.chunk_bytes[pc]);
+                bulk_load(slots + (size_t)slot * dm.slot_bytes, img + ts.chunk_off[pc], (uint32_t)ts.chunk_bytes[pc], &bars->full[slot]);
             }
             __syncwarp();
         }
@@ -259,8 +272,8 @@ __device__ __forceinline__ void t3_issuer(const T2Step* __restrict__ steps, cons
     const int lane = threadIdx.x & 31;
     uint32_t ring_it = 0;
     uint32_t opnd_c0 = 0, opnd_c1 = 0, fin_c0 = 0, fin_c1 = 0;    // per-tile phase counters
-    T3_ITEM_BEGIN
-    T3_STEP_BEGIN
+    T3_ITEM_BEGIN(dm.seq)
+    T3_STEP_BEGIN(dm.seq)
         const uint32_t base = ring_it;
 #pragma unroll 1
         for (int ci = net; ci < ts.nchunks; ci += 2) {
@@ -268,12 +281,13 @@ __device__ __forceinline__ void t3_issuer(const T2Step* __restrict__ steps, cons
             mbar_wait(&bars->full[it & smask], (it >> dm.nslots_log2) & 1u);
             const int w = ts.job_wait[ci], src = ts.job_src[ci], Kp = ts.job_kp[ci], N = ts.job_n[ci];
             const bool has_bias_tile = ts.job_fold[ci] != 0, fold = has_bias_tile && !dm.no_fold;
+            const int chunk_bytes = ts.chunk_bytes[t3_chunk_of_job(ts, ci, dm.seq == 2)];
             const uint8_t* chunk = slots + (size_t)(it & smask) * dm.slot_bytes;
             const uint32_t b_hi = smem_u32(chunk);
             {   // the fp32 tail (biases, last-row vector) moves to the bias ring so that the weight slot can be handed
                 // back as soon as the MMAs that read it complete (tcgen05.commit -> empty), not after the epilogue
                 const int tiles_b = (NPASS == 3 ? 2 : 1) * N * Kp * 2;
-                const int n16 = (ts.chunk_bytes[ci] - tiles_b - (has_bias_tile ? N * 32 : 0)) >> 4;
+                const int n16 = (chunk_bytes - tiles_b - (has_bias_tile ? N * 32 : 0)) >> 4;
                 const float4* srcp = reinterpret_cast<const float4*>(chunk + tiles_b);
                 float4* dstp = reinterpret_cast<float4*>(bias_ring + (size_t)(net * 4 + ((it >> 1) & 3)) * kT3BiasEntry);
                 for (int q = lane; q < n16; q += 32) dstp[q] = srcp[q];
@@ -284,7 +298,7 @@ __device__ __forceinline__ void t3_issuer(const T2Step* __restrict__ steps, cons
             const int nk = Kp >> 4;
             // folded bias: acc = ones[128 x 16] * bias_tile[N x 16]^T first, everything else accumulates on top
             const uint64_t d_ones = umma_desc(smem_u32(m.ones), 128, 256u);
-            const uint64_t d_bias = umma_desc(b_hi + (uint32_t)(ts.chunk_bytes[ci] - N * 32), 128, 256u);
+            const uint64_t d_bias = umma_desc(b_hi + (uint32_t)(chunk_bytes - N * 32), 128, 256u);
             const uint32_t acc0 = fold ? 1u : 0u;
             uint32_t leader;
             asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(leader));
@@ -341,10 +355,14 @@ __device__ __forceinline__ void t3_issuer(const T2Step* __restrict__ steps, cons
 
 // ===== compute groups: group g owns tile 2*pair + g; thread = (row, column part) =====
 // FOLD_D / FOLD_C: the density / coupling hidden layers of every step of this launch carry folded biases
-template <int NPASS, bool FOLD_D, bool FOLD_C>
-__device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, const RowArgs& a, const T3Dims& dm, long long pairs_per_step,
-                                        long long total_items, uint8_t* smem, uint32_t tmem_base) {
+// INV: the sampler (flow.sample_with_log_prob, fastpredNF.py:586-607): every step runs CIF_step.inverse -- sample u from
+// q, undo the blocks last to first, score u under r -- and the point / prefix come from the row's own samples.
+// MODE (compile-time copy of T3Dims::seq for this role): 0 per-step density, 1 chain, 2 sampler
+template <int NPASS, bool FOLD_D, bool FOLD_C, int MODE>
+__device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, const RowArgs& a, const SampleOut& o, const T3Dims& dm,
+                                        long long pairs_per_step, long long total_items, uint8_t* smem, uint32_t tmem_base) {
     constexpr int NPARTS = 2;
+    constexpr bool INV = MODE == 2;
     const T3Smem m = t3_smem(smem, dm);
     Bars3* bars = m.bars;
     uint8_t* bias_ring = m.bias_ring;
@@ -359,30 +377,43 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
     x.bias_ring = smem_u32(bias_ring);
     x.h_stride = h_stride;
     x.h_base = smem_u32(m.hbuf) + (uint32_t)x.g * 4u * h_stride;
-    T3_ITEM_BEGIN
+    T3_ITEM_BEGIN(MODE)
         const int g = x.g;
         long long n = (pair * 2 + g) * 128 + x.row;
         const bool valid = n < a.N;
         if (!valid) n = a.N - 1;
         const long long ag = n / a.PPA, rem = n % a.PPA, pt = rem / a.K;
-        float z0, z1, prev0, prev1, lacc = 0.0f;
-        {
+        float z0, z1, prev0, prev1, lacc = 0.0f, base_lp = 0.0f, cum = 0.0f;
+        if (INV) {      // u0 ~ Normal(base_pos, std[0]) (Normal.sample = normal_() * std + mean), its log-density
+            const float* pp = src_at(a.base, ag, pt, 0);
+            prev0 = __ldg(pp); prev1 = __ldg(pp + 1);
+            const float s0 = __ldg(&steps[0].std[0]), s1 = __ldg(&steps[0].std[1]);
+            float e0, e1;
+            if (a.z0 != nullptr) { e0 = __ldg(a.z0 + n * 2); e1 = __ldg(a.z0 + n * 2 + 1); }
+            else { const float4 gq = philox_normal4(a.seed, n, 0xFFFFu, 0u); e0 = gq.x; e1 = gq.y; }
+            z0 = __fadd_rn(__fmul_rn(e0, s0), prev0); z1 = __fadd_rn(__fmul_rn(e1, s1), prev1);
+            base_lp = normal_lp2(z0, z1, prev0, prev1, s0, s1);
+            if (valid && x.part == 0) o.base_lp[n] = base_lp;
+        } else {
             const float* xp = src_at(a.x, ag, pt, jstep);
             z0 = __ldg(xp); z1 = __ldg(xp + 1);
             // base mean: per-step mode = previous trajectory point; chain mode = base_pos (fastpredNF.py:454-458)
-            const float* pp = (dm.seq || jstep == 0) ? src_at(a.base, ag, pt, 0) : src_at(a.prefix, ag, pt, jstep - 1);
+            const float* pp = (MODE == 1 || jstep == 0) ? src_at(a.base, ag, pt, 0) : src_at(a.prefix, ag, pt, jstep - 1);
             prev0 = __ldg(pp); prev1 = __ldg(pp + 1);
         }
-    T3_STEP_BEGIN
+    T3_STEP_BEGIN(MODE)
         const int C = ts.C, c = ts.c, Kin = ts.Kin, Ku = ts.Ku, Wd = ts.Wd, CPd = ts.CPd, Hc = ts.Hc;
+        if (INV) lacc = 0.0f;       // the sampler reports every step's own log-det term
         // byte offset of this row inside a canonical [128 x W] operand tile, for the two hidden widths of the step
         const uint32_t koff_d = (uint32_t)((x.row >> 3) * (Wd >> 3) * 128 + (x.row & 7) * 16);
         const uint32_t koff_c = (uint32_t)((x.row >> 3) * (Hc >> 3) * 128 + (x.row & 7) * 16);
         // ---- input operand [z (2), cond (C0), prefix (2*step), 0...] ----
         {
-            const float* cp = src_at(a.cond, ag, pt, jstep) - 2;     // chain mode: cond[:, j] for every chain step
-            const float* pf = src_at(a.prefix, ag, pt, 0);
-            const long long pst = a.prefix.st;
+            const float* cp = src_at(a.cond, ag, pt, INV ? step : jstep) - 2;     // chain mode: cond[:, j] for every chain step
+            // sampler: the prefix is the row's own earlier samples, read back from the output (written by this group's
+            // part-0 threads before the CTA-wide barrier of the step-table reload; coherent loads, not the read-only path)
+            const float* pf = INV ? o.seq + n * (long long)(2 * dm.T) : src_at(a.prefix, ag, pt, 0);
+            const long long pst = INV ? 2 : a.prefix.st;
             const int c0e = 2 + dm.C0;
             for (int k0 = x.part * 8; k0 < Kin; k0 += 8 * NPARTS) {
                 float v[8];
@@ -392,7 +423,7 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
                     float val = 0.0f;
                     if (col < 2) val = col == 0 ? z0 : z1;
                     else if (col < c0e) val = __ldg(cp + col);
-                    else if (col < c) { const int e = col - c0e; val = __ldg(pf + (long long)(e >> 1) * pst + (e & 1)); }
+                    else if (col < c) { const int e = col - c0e; const float* q = pf + (long long)(e >> 1) * pst + (e & 1); val = INV ? __ldcg(q) : __ldg(q); }
                     v[i] = clamp_h(val);
                 }
                 uint32_t hi[4], lo[4];
@@ -427,7 +458,13 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
             wait_mma3(x, 1);
             if (which == 0) {
                 // sample u = exp(ls) eps + mu (fastpredNF.py:727-733) -> [u, mx] operand; log r = -C/2 log 2pi - sum ls - 1/2 sum eps^2
-                const int m0 = ts.masked_dim[0];
+                if (INV) {      // modules reversed: the last block's BatchNorm.inverse comes first (TFCondARFlow.py:264-269)
+                    const int bl = ts.n_blocks - 1;
+                    z0 = fmaf(ts.bn_iscale[bl][0], z0, ts.bn_ishift[bl][0]);
+                    z1 = fmaf(ts.bn_iscale[bl][1], z1, ts.bn_ishift[bl][1]);
+                    lacc -= ts.bn_ldj[bl];
+                }
+                const int m0 = ts.masked_dim[INV ? ts.n_blocks - 1 : 0];
                 float p_ls = 0.0f, p_e2 = 0.0f;
                 for (int d0 = x.part * 8; d0 < Ku; d0 += 8 * NPARTS) {
                     float u[8];
@@ -440,11 +477,11 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
                         tmem_ld8(x.tb + kT3Acc0 + (uint32_t)d0, mu);
                         tmem_ld8(x.tb + kT3Acc1 + (uint32_t)d0, ls);
                         if (a.eps != nullptr) {
-                            const float* ep = a.eps + n * a.eps_rs + (dm.seq ? ts.seq_eps_off + (jstep - step) * C : ts.eps_off) + d0;
+                            const float* ep = a.eps + n * a.eps_rs + (MODE == 1 ? ts.seq_eps_off + (jstep - step) * C : ts.eps_off) + d0;
 #pragma unroll
                             for (int i = 0; i < 8; ++i) if (d0 + i < C) e[i] = __ldg(ep + i);
                         } else {
-                            const Normal8 gn = philox_normal8(a.seed, n, dm.seq ? (unsigned)(step * 64 + jstep + 4096) : (unsigned)step, (unsigned)(d0 >> 2));
+                            const Normal8 gn = philox_normal8(a.seed, n, MODE == 1 ? (unsigned)(step * 64 + jstep + 4096) : (unsigned)step, (unsigned)(d0 >> 2));
                             e[0] = gn.a.x; e[1] = gn.a.y; e[2] = gn.a.z; e[3] = gn.a.w; e[4] = gn.b.x; e[5] = gn.b.y; e[6] = gn.b.z; e[7] = gn.b.w;
                         }
                         tmem_wait_ld();
@@ -470,7 +507,8 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
                     tmem_st4(x.tb + kT3ULo + (uint32_t)(d0 >> 1), lo);
                 }
                 const float s_ls = row_sum3(x, 0, p_ls), s_e2 = row_sum3(x, 1, p_e2);
-                lacc -= (-0.5f * (float)C * kLog2Pi - s_ls) - 0.5f * s_e2;
+                const float lp_u = (-0.5f * (float)C * kLog2Pi - s_ls) - 0.5f * s_e2;      // log density of the drawn u
+                lacc += INV ? lp_u : -lp_u;                                                // forward: -log r, inverse: +log q
             } else {
                 // log q(u | w, y) (fastpredNF.py:713-724), u reconstructed from its hi+lo operand
                 float p_ls = 0.0f, p_q = 0.0f;
@@ -496,14 +534,16 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
                     }
                 }
                 const float s_ls = row_sum3(x, 0, p_ls), s_q = row_sum3(x, 1, p_q);
-                lacc += (-0.5f * (float)C * kLog2Pi - s_ls) - 0.5f * s_q;
+                const float lp_u = (-0.5f * (float)C * kLog2Pi - s_ls) - 0.5f * s_q;
+                lacc += INV ? -lp_u : lp_u;                                                // forward: +log q, inverse: -log r
             }
             warp_arrive3(x, &bars->fin[g]);
             if (which == 1) break;
 
             // ============ n_blocks x (masked affine coupling + BatchNorm), forward ============
 #pragma unroll 1
-            for (int b = 0; b < ts.n_blocks; ++b) {
+            for (int bi = 0; bi < ts.n_blocks; ++bi) {
+                const int b = INV ? ts.n_blocks - 1 - bi : bi;
                 const int j = 1 - ts.masked_dim[b];
                 float ps = 0.0f, pt_ = 0.0f, bs = 0.0f, bt = 0.0f;
 #pragma unroll 1
@@ -531,16 +571,27 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
                 // both nets done: affine update of the unmasked coordinate + BatchNorm (TFCondARFlow.py:360-381, 303-315)
                 const float s = row_sum3(x, 0, ps) + bs, t = row_sum3(x, 1, pt_) + bt;
                 const float log_s = tanhf(s);
-                if (j == 0) z0 = fmaf(z0, expf(log_s), t); else z1 = fmaf(z1, expf(log_s), t);
-                z0 = fmaf(ts.bn_scale[b][0], z0, ts.bn_shift[b][0]);
-                z1 = fmaf(ts.bn_scale[b][1], z1, ts.bn_shift[b][1]);
-                lacc += log_s + ts.bn_ldj[b];
-                const bool more = b + 1 < ts.n_blocks;
+                const bool more = bi + 1 < ts.n_blocks;
+                const int bn = INV ? b - 1 : b + 1;                  // the block processed next
+                if (!INV) {
+                    if (j == 0) z0 = fmaf(z0, expf(log_s), t); else z1 = fmaf(z1, expf(log_s), t);
+                    z0 = fmaf(ts.bn_scale[b][0], z0, ts.bn_shift[b][0]);
+                    z1 = fmaf(ts.bn_scale[b][1], z1, ts.bn_shift[b][1]);
+                    lacc += log_s + ts.bn_ldj[b];
+                } else {            // x = (u - t) exp(-log_s) (TFCondARFlow.py:383-402), then the next block's BatchNorm.inverse
+                    if (j == 0) z0 = (z0 - t) * expf(-log_s); else z1 = (z1 - t) * expf(-log_s);
+                    lacc -= log_s;
+                    if (more) {
+                        z0 = fmaf(ts.bn_iscale[bn][0], z0, ts.bn_ishift[bn][0]);
+                        z1 = fmaf(ts.bn_iscale[bn][1], z1, ts.bn_ishift[bn][1]);
+                        lacc -= ts.bn_ldj[bn];
+                    }
+                }
                 float p0, p1;
                 uint32_t dst_hi, dst_lo;
                 int owner;
                 if (more) {
-                    const int mn = ts.masked_dim[b + 1];
+                    const int mn = ts.masked_dim[bn];
                     p0 = mn == 0 ? clamp_h(z0) : 0.0f; p1 = mn == 1 ? clamp_h(z1) : 0.0f;
                     dst_hi = kT3UHi + (uint32_t)(C >> 1); dst_lo = kT3ULo + (uint32_t)(C >> 1);
                     owner = (C >> 3) % NPARTS;
@@ -559,9 +610,18 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
                 warp_arrive3(x, &bars->fin[g]);
             }
         }
+        if (INV) {      // z = the sample of this step; log_prob = base + running mean of the step terms (fastpredNF.py:598-607)
+            cum += lacc;
+            if (valid && x.part == 0) {
+                const long long q = n * dm.T + step;
+                o.seq[q * 2] = z0; o.seq[q * 2 + 1] = z1;
+                o.ldjs[q] = lacc;
+                o.log_prob[q] = base_lp + cum / (float)(step + 1);
+            }
+        }
     T3_STEP_END
-        if (valid && x.part == 0) {
-            if (!dm.seq) {
+        if (!INV && valid && x.part == 0) {
+            if (MODE == 0) {
                 const float lp = normal_lp2(z0, z1, prev0, prev1, m.cur->std[0], m.cur->std[1]) + lacc;
                 a.out[ag * a.out_sa + rem * a.out_sp + (long long)jstep * a.out_st] = lp;
             } else {      // base = Normal(base_pos, std[0]); ldj = mean over the chain steps of this result index
@@ -574,10 +634,10 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
 
 }  // namespace t3
 
-template <int NPASS, bool FOLD_D, bool FOLD_C>
+template <int NPASS, bool FOLD_D, bool FOLD_C, int MODE = 0>
 __global__ void __launch_bounds__(kT3Threads, 1)
 k_separate_tc3(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img, const __grid_constant__ RowArgs a,
-               const __grid_constant__ T3Dims dm, long long pairs_per_step, long long total_items) {
+               const __grid_constant__ T3Dims dm, long long pairs_per_step, long long total_items, const __grid_constant__ SampleOut o) {
     using namespace tc;
     using namespace t2;
     using namespace t3;
@@ -616,7 +676,7 @@ k_separate_tc3(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tslot);
 
     // three roles (inlined: separate noinline role functions measured 3 ms slower)
-    if (warp < 16) t3_compute<NPASS, FOLD_D, FOLD_C>(steps, a, dm, pairs_per_step, total_items, smem, tmem_base);
+    if (warp < 16) t3_compute<NPASS, FOLD_D, FOLD_C, MODE>(steps, a, o, dm, pairs_per_step, total_items, smem, tmem_base);
     else if (warp == 16) t3_producer(steps, img, dm, pairs_per_step, total_items, smem);
     else t3_issuer<NPASS>(steps, dm, pairs_per_step, total_items, smem, tmem_base, warp - 17);
 
@@ -665,7 +725,7 @@ inline int tc3_launch_separate(const T2Dims& dm2, const std::vector<T2Step>& hst
         cudaError_t e = cudaSuccess;
         auto go = [&](auto kern) {
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess) kern<<<grid, kT3Threads, smem, stream>>>(d_steps, d_img, a, dm, pairs, items);
+            if (e == cudaSuccess) kern<<<grid, kT3Threads, smem, stream>>>(d_steps, d_img, a, dm, pairs, items, SampleOut{});
         };
         if (fold_d && fold_c) go(k_separate_tc3<NPASS, true, true>);
         else if (fold_c) go(k_separate_tc3<NPASS, false, true>);
@@ -703,15 +763,48 @@ inline int tc3_launch_sequential(const T2Dims& dm2, const std::vector<T2Step>& h
     dm.nslots_log2 = (fixed + (size_t)4 * slot <= (size_t)smem_optin) ? 2 : 1;
     const size_t smem = fixed + ((size_t)1 << dm.nslots_log2) * slot;
     if (wc > 80 || smem > (size_t)smem_optin) { *msg = "the tensor-core chain kernel does not fit this model shape; use FC_PREC_FP32"; return 1; }
-    auto kern = k_separate_tc3<NPASS, false, false>;
+    auto kern = k_separate_tc3<NPASS, false, false, 1>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { *msg = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return 1; }
     const long long items = pairs * (T - a.seq_jlo);
     const int grid = (int)(items < num_sms ? items : num_sms);
-    kern<<<grid, kT3Threads, smem, stream>>>(d_steps, d_img, a, dm, pairs, items);
+    kern<<<grid, kT3Threads, smem, stream>>>(d_steps, d_img, a, dm, pairs, items, SampleOut{});
     (*launches)++;
     e = cudaGetLastError();
     if (e != cudaSuccess) { *msg = std::string("k_separate_tc3 (chain) launch: ") + cudaGetErrorString(e); return 1; }
+    return 0;
+}
+
+// Sampler (flow.sample_with_log_prob): one launch, item = tile pair, steps 0 .. T-1 in the inverse direction.
+template <int NPASS>
+inline int tc3_launch_sample(const T2Dims& dm2, const std::vector<T2Step>& hsteps, const T2Step* d_steps, const unsigned char* d_img,
+                             const RowArgs& a, const SampleOut& o, int num_sms, int smem_optin, cudaStream_t stream, uint64_t* launches,
+                             std::string* msg) {
+    if (!dm2.supported || d_img == nullptr) { *msg = "the tensor-core path does not support this model shape; use FC_PREC_FP32"; return 1; }
+    const int T = dm2.T;
+    const long long tiles = (a.N + 127) / 128, pairs = (tiles + 1) / 2;
+    int wc = 64, slot = 0;
+    for (int s = 0; s < T; ++s) {
+        const int w = hsteps[s].Wd > hsteps[s].Hc ? hsteps[s].Wd : hsteps[s].Hc;
+        wc = w > wc ? w : wc;
+        for (int ci = 0; ci < hsteps[s].nchunks; ++ci) slot = hsteps[s].chunk_bytes[ci] > slot ? hsteps[s].chunk_bytes[ci] : slot;
+    }
+    slot = (slot + 127) / 128 * 128;
+    T3Dims dm{};
+    dm.slot_bytes = slot; dm.Wmax = wc; dm.T = T; dm.C0 = dm2.C0; dm.step_lo = 0; dm.step_hi = T - 1;
+    dm.seq = 2; dm.no_fold = 1;
+    const size_t fixed = (size_t)kT3Header + (size_t)8 * 128 * wc * 2;
+    dm.nslots_log2 = (fixed + (size_t)4 * slot <= (size_t)smem_optin) ? 2 : 1;
+    const size_t smem = fixed + ((size_t)1 << dm.nslots_log2) * slot;
+    if (wc > 80 || smem > (size_t)smem_optin) { *msg = "the tensor-core sampler does not fit this model shape; use FC_PREC_FP32"; return 1; }
+    auto kern = k_separate_tc3<NPASS, false, false, 2>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { *msg = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return 1; }
+    const int grid = (int)(pairs < num_sms ? pairs : num_sms);
+    kern<<<grid, kT3Threads, smem, stream>>>(d_steps, d_img, a, dm, pairs, pairs, o);
+    (*launches)++;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { *msg = std::string("k_separate_tc3 (sampler) launch: ") + cudaGetErrorString(e); return 1; }
     return 0;
 }
 

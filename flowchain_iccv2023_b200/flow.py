@@ -210,12 +210,13 @@ class fastpredNF_CIF_separate_cond(nn.Module):
         return out.to(src)
 
     @torch.no_grad()
-    def sample_with_log_prob(self, base_pos, cond, z0=None, eps=None, seed=None):
+    def sample_with_log_prob(self, base_pos, cond, z0=None, eps=None, seed=None, precision=None):
         """fastpredNF.sample_with_log_prob (fastpredNF.py:472-477).
 
         Accepts the reference's expanded arguments base_pos (B,S,2), cond (B,S,T,C0) (stride-0
         expands are fine: only [:,0] is read -- the reference passes per-agent values expanded over
-        S, fastpredNF.py:106-108).  Returns (seq (B,S,T,2), log_prob (B,S,T), ldjs (B,S,T), base_lp (B,S,1))."""
+        S, fastpredNF.py:106-108).  Returns (seq (B,S,T,2), log_prob (B,S,T), ldjs (B,S,T), base_lp (B,S,1)).
+        `precision`: FC_PREC_FP32 (CUDA-core sampler) or FC_PREC_F16X3 / FC_PREC_F16 (tensor-core sampler)."""
         h = self.engine()
         src = base_pos.device
         if base_pos.dim() != 3 or cond.dim() != 4:
@@ -225,7 +226,10 @@ class fastpredNF_CIF_separate_cond(nn.Module):
         cd = self._dev(cond[:, 0])
         z0 = None if z0 is None else self._dev(z0).reshape(B * S, 2)
         eps = None if eps is None else self._dev(eps).reshape(B * S, -1)
-        outs = torch.ops.flowchain.sample_with_log_prob(h.id, bp, cd, S, z0, eps, self._seed(seed), _lib.FC_PREC_FP32)
+        prec = self.precision if precision is None else precision
+        if prec == _lib.FC_PREC_BF16:        # the bf16 single-pass kernel implements the per-step density only
+            prec = _lib.FC_PREC_FP32
+        outs = torch.ops.flowchain.sample_with_log_prob(h.id, bp, cd, S, z0, eps, self._seed(seed), prec)
         return tuple(o.to(src) for o in outs)
 
     @torch.no_grad()
