@@ -305,7 +305,7 @@ def run_ours(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32", "bf16": "bf16 operands / f32 accumulate", "f16": "f16 operands / f32 accumulate",
                       "f16x3": "split-f16 operands (3 tcgen05 passes) / f32 accumulate"}[args.precision], "data": "synthetic",
-            "config": {"workload": f"config2: {A} agents x {T} steps x {n}x{n} lattice per GPU, separate density (flow.log_prob), prefix self",
+            "config": {"workload": f"{'config2' if (A, n) == (64, 256) else ('config4 shard' if n == 512 else 'custom')}: {A} agents x {T} steps x {n}x{n} lattice per GPU, separate density (flow.log_prob), prefix self",
                        "model": "default ETH CIF_separate_cond (T=12,C0=16,H=64,3 blocks), random-init weights",
                        "noise": "in-kernel Philox4x32-10", "precision": args.precision,
                        "l2": "L2 flushed (256 MB write) between timed iterations; output 201 MB > L2",
