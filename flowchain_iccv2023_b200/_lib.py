@@ -21,7 +21,7 @@ FC_PREFIX_SHARED = 1
 
 SYMBOLS = [
     "fc_create", "fc_destroy", "fc_last_error", "fc_weight_blob_floats", "fc_load_weights",
-    "fc_weights_version", "fc_log_prob", "fc_log_prob_sequential", "fc_grid_log_prob",
+    "fc_weights_version", "fc_log_prob", "fc_log_prob_sequential", "fc_grid_log_prob", "fc_grid_log_prob_multicast",
     "fc_sample_with_log_prob", "fc_base_normalizer", "fc_update", "fc_launch_count", "fc_tc_gemm_selftest",
 ]
 
@@ -64,6 +64,9 @@ def load():
     lib.fc_grid_log_prob.argtypes = [c_void_p, fp, fp, fp, fp, fp, c_uint64, c_int, c_int, c_int, fp,
                                      c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p]
     lib.fc_grid_log_prob.restype = c_int
+    lib.fc_grid_log_prob_multicast.argtypes = [c_void_p, fp, fp, fp, fp, fp, c_uint64, c_int, c_int, fp,
+                                               c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p]
+    lib.fc_grid_log_prob_multicast.restype = c_int
     lib.fc_sample_with_log_prob.argtypes = [c_void_p, fp, fp, fp, fp, c_uint64, fp, fp, fp, fp,
                                             c_int64, c_int64, c_int, c_void_p]
     lib.fc_sample_with_log_prob.restype = c_int

@@ -433,11 +433,12 @@ extern "C" int fc_log_prob_sequential(fc_handle* h, const float* base_pos, const
     return launch_density(h, a, MODE_SEQUENTIAL, precision, (cudaStream_t)stream);
 }
 
-extern "C" int fc_grid_log_prob(fc_handle* h, const float* base_pos, const float* cond, const float* cond_traj,
-                                const float* grid, const float* eps, uint64_t seed, int prefix_mode, int sequential,
-                                int K, float* out, int64_t out_agent_stride, int64_t out_point_stride,
-                                int64_t out_step_stride, int64_t A, int64_t G, int precision, void* stream_) {
+static int grid_log_prob_impl(fc_handle* h, const float* base_pos, const float* cond, const float* cond_traj,
+                              const float* grid, const float* eps, uint64_t seed, int prefix_mode, int sequential,
+                              int K, float* out, int64_t out_agent_stride, int64_t out_point_stride,
+                              int64_t out_step_stride, int64_t A, int64_t G, int precision, void* stream_, int multicast) {
     if (ready(h)) return 1;
+    if (multicast && K != 1) return fail(h, "multicast output supports K = 1 only");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (A < 0 || G < 0) return fail(h, "negative size");
     if (K < 1 || K > 4096) return fail(h, "K must be in [1, 4096], got %d", K);
@@ -454,6 +455,7 @@ extern "C" int fc_grid_log_prob(fc_handle* h, const float* base_pos, const float
     a.eps = eps; a.eps_rs = sequential ? h->Eseq : h->E; a.seed = seed;
     a.N = A * G * K; a.PPA = G * K; a.K = K;
     a.seq_klo = 0; a.seq_jlo = 0;
+    a.out_sys = multicast ? 1 : 0;
     if (K == 1) {
         a.out = out; a.out_sa = out_agent_stride; a.out_sp = out_point_stride; a.out_st = out_step_stride;
         return launch_density(h, a, sequential ? MODE_SEQUENTIAL : MODE_SEPARATE, precision, stream);
@@ -474,6 +476,22 @@ extern "C" int fc_grid_log_prob(fc_handle* h, const float* base_pos, const float
     h->launches++;
     FC_CUDA(h, cudaGetLastError());
     return 0;
+}
+
+extern "C" int fc_grid_log_prob(fc_handle* h, const float* base_pos, const float* cond, const float* cond_traj,
+                                const float* grid, const float* eps, uint64_t seed, int prefix_mode, int sequential,
+                                int K, float* out, int64_t out_agent_stride, int64_t out_point_stride,
+                                int64_t out_step_stride, int64_t A, int64_t G, int precision, void* stream) {
+    return grid_log_prob_impl(h, base_pos, cond, cond_traj, grid, eps, seed, prefix_mode, sequential, K, out, out_agent_stride,
+                              out_point_stride, out_step_stride, A, G, precision, stream, 0);
+}
+
+extern "C" int fc_grid_log_prob_multicast(fc_handle* h, const float* base_pos, const float* cond, const float* cond_traj,
+                                          const float* grid, const float* eps, uint64_t seed, int prefix_mode, int sequential,
+                                          float* out_multicast, int64_t out_agent_stride, int64_t out_point_stride,
+                                          int64_t out_step_stride, int64_t A, int64_t G, int precision, void* stream) {
+    return grid_log_prob_impl(h, base_pos, cond, cond_traj, grid, eps, seed, prefix_mode, sequential, 1, out_multicast,
+                              out_agent_stride, out_point_stride, out_step_stride, A, G, precision, stream, 1);
 }
 
 extern "C" int fc_sample_with_log_prob(fc_handle* h, const float* base_pos, const float* cond, const float* z0,

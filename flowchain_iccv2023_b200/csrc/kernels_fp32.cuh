@@ -444,7 +444,7 @@ k_separate_fp32(const StepPlan* __restrict__ plans, const float* __restrict__ wb
     if (r < R && row0 + r < a.N) {
         const float lp = normal_lp2(t.Z[r], t.Z[R + r], t.PREV[r], t.PREV[R + r], t.sp->std[0], t.sp->std[1]) + t.ACC[r];
         const long long n = row0 + r;
-        a.out[t.ROWA[r] * a.out_sa + (n % a.PPA) * a.out_sp + (long long)step * a.out_st] = lp;
+        store_out(a, t.ROWA[r] * a.out_sa + (n % a.PPA) * a.out_sp + (long long)step * a.out_st, lp);
     }
 }
 
@@ -483,7 +483,7 @@ k_sequential_fp32(const StepPlan* __restrict__ plans, const float* __restrict__ 
         const float lp = normal_lp2(t.Z[r], t.Z[R + r], t.PREV[r], t.PREV[R + r], s0, s1) +
                          t.ACC[r] / (float)(j - a.seq_jlo + 1);
         const long long n = row0 + r;
-        a.out[t.ROWA[r] * a.out_sa + (n % a.PPA) * a.out_sp + (long long)(j - a.seq_jlo) * a.out_st] = lp;
+        store_out(a, t.ROWA[r] * a.out_sa + (n % a.PPA) * a.out_sp + (long long)(j - a.seq_jlo) * a.out_st, lp);
     }
 }
 

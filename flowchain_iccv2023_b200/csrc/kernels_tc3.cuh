@@ -623,10 +623,10 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
         if (!INV && valid && x.part == 0) {
             if (MODE == 0) {
                 const float lp = normal_lp2(z0, z1, prev0, prev1, m.cur->std[0], m.cur->std[1]) + lacc;
-                a.out[ag * a.out_sa + rem * a.out_sp + (long long)jstep * a.out_st] = lp;
+                store_out(a, ag * a.out_sa + rem * a.out_sp + (long long)jstep * a.out_st, lp);
             } else {      // base = Normal(base_pos, std[0]); ldj = mean over the chain steps of this result index
                 const float lp = normal_lp2(z0, z1, prev0, prev1, __ldg(&steps[0].std[0]), __ldg(&steps[0].std[1])) + lacc / (float)(jstep - dm.jlo + 1);
-                a.out[ag * a.out_sa + rem * a.out_sp + (long long)(jstep - dm.jlo) * a.out_st] = lp;
+                store_out(a, ag * a.out_sa + rem * a.out_sp + (long long)(jstep - dm.jlo) * a.out_st, lp);
             }
         }
     T3_ITEM_END

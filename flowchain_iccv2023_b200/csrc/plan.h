@@ -66,7 +66,17 @@ struct RowArgs {
     long long out_sa, out_sp, out_st;
     int seq_klo;           // sequential: lowest chain step applied (0, or T - n_step)
     int seq_jlo;           // sequential: first result index written (0, or T - n_step - 1)
+    int out_sys;           // 1: `out` is an NVSwitch multicast address of a symmetric buffer: every store is replicated to
+                           // all peers, so the density maps are all-gathered by the stores themselves (system-scope stores)
 };
+
+#ifdef __CUDACC__
+// the one place a log-density leaves the chip
+__device__ __forceinline__ void store_out(const RowArgs& a, long long idx, float v) {
+    if (a.out_sys) asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(a.out + idx), "f"(v) : "memory");
+    else a.out[idx] = v;
+}
+#endif
 
 struct SampleOut {
     float* seq;       // (N, T, 2)

@@ -5,6 +5,11 @@ path shards with NO data-path collective: packed weights (4.4 MB) are replicated
 contiguous blocks over ranks (grid tiles when there are fewer agents than ranks), and ONE all-gather
 assembles the (A, T, G) density maps.  One process per GPU, ``torch.distributed`` (NCCL on GPUs, gloo in
 the CPU tests) is plumbing only.
+
+On an NVSwitch box the all-gather is fused into the density kernel (`MulticastMaps`): the maps live in a
+symmetric buffer with a multicast mapping and the kernel's result stores go to the multicast address, so the
+switch replicates every store to all peers while the kernel is still computing; what remains after the kernel
+is one cross-rank barrier.  The NCCL all-gather is the fallback (no multicast support, gloo tests).
 """
 from __future__ import annotations
 
@@ -59,6 +64,44 @@ def gather_point_maps(local: torch.Tensor, sizes, group=None) -> torch.Tensor:
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return local
     return _gather(local, list(sizes), 2, group)
+
+
+class MulticastMaps:
+    """Symmetric (A, T, G) density-map buffer, one replica per rank, with an NVSwitch multicast address.
+
+    `fill(flow, ...)` evaluates this rank's shard with `fc_grid_log_prob_multicast`: the kernel's stores are replicated
+    by the switch into every rank's replica, then one symmetric-memory barrier makes them readable everywhere.
+    Raises RuntimeError when the platform has no multicast support (callers fall back to `sharded_grid_log_prob`)."""
+
+    def __init__(self, agents: int, steps: int, points: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        grp = dist.group.WORLD if group is None else group
+        self.group = grp
+        self.shape = (agents, steps, points)
+        self.maps = symm.empty(self.shape, dtype=torch.float32, device=device)
+        self.handle = symm.rendezvous(self.maps, grp.group_name)
+        self.mc_ptr = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        if self.mc_ptr == 0:
+            raise RuntimeError("symmetric memory has no multicast mapping on this platform")
+
+    def barrier(self):
+        self.handle.barrier()
+
+    def fill(self, flow, base_pos, cond, grid, cond_traj=None, **kw) -> torch.Tensor:
+        """Inputs are the FULL per-agent tensors (replicated, tiny).  Returns this rank's replica of the full maps."""
+        A, T, G = self.shape
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        mode, ranges = plan_shards(A, G, world)
+        lo, hi = ranges[rank]
+        self.barrier()          # nobody is still reading the previous maps
+        if mode == "agents":
+            flow.grid_log_prob_multicast(base_pos[lo:hi], cond[lo:hi], grid, self.mc_ptr, lo * T * G, (T * G, 1, G),
+                                         cond_traj=None if cond_traj is None else cond_traj[lo:hi], **kw)
+        else:
+            flow.grid_log_prob_multicast(base_pos, cond, grid[lo:hi].contiguous(), self.mc_ptr, lo, (T * G, 1, G),
+                                         cond_traj=cond_traj, **kw)
+        self.barrier()          # every rank's stores have landed in every replica
+        return self.maps
 
 
 def sharded_grid_log_prob(flow, base_pos, cond, grid, cond_traj=None, group=None, **kw) -> torch.Tensor:

@@ -248,5 +248,19 @@ class fastpredNF_CIF_separate_cond(nn.Module):
             bool(map_layout), self.precision if precision is None else precision)
         return out.to(src)
 
+    @torch.no_grad()
+    def grid_log_prob_multicast(self, base_pos, cond, grid, mc_ptr, offset_elems, strides, cond_traj=None,
+                                sequential=False, seed=None, precision=None):
+        """`grid_log_prob` of this rank's shard with the results stored through an NVSwitch multicast address
+        (`dist.MulticastMaps`): element (a, g, t) lands at `offset_elems + a*strides[0] + g*strides[1] + t*strides[2]` of
+        EVERY rank's symmetric map buffer.  Returns nothing; call the buffer's barrier before reading."""
+        from . import ops
+        h = self.engine()
+        ops.grid_log_prob_multicast(
+            h.id, self._dev(base_pos), self._dev(cond), self._dev(cond_traj), self._dev(grid), self._seed(seed),
+            _lib.FC_PREFIX_SELF if cond_traj is None else _lib.FC_PREFIX_SHARED, bool(sequential), int(mc_ptr),
+            int(offset_elems), int(strides[0]), int(strides[1]), int(strides[2]),
+            self.precision if precision is None else precision)
+
     def forward(self, *a, **k):
         return _Fused.forward(self)

@@ -172,6 +172,24 @@ def _(hid, base_pos, cond, cond_traj, grid, eps, seed, prefix_mode, sequential, 
     return grid.new_empty((A, T, G) if map_layout else (A, G, T))
 
 
+def grid_log_prob_multicast(hid: int, base_pos: torch.Tensor, cond: torch.Tensor, cond_traj: Optional[torch.Tensor],
+                            grid: torch.Tensor, seed: int, prefix_mode: int, sequential: bool, mc_ptr: int,
+                            offset_elems: int, sa: int, sp: int, st: int, precision: int) -> None:
+    """fc_grid_log_prob_multicast: the (a, g, t) results are stored to `mc_ptr + 4*(offset_elems + a*sa + g*sp + t*st)`,
+    an NVSwitch multicast address, so every rank's symmetric map buffer receives them (no all-gather afterwards).
+    Not a torch custom op: the destination is a raw multicast address, not a tensor; the caller owns the barrier."""
+    h = _h(hid)
+    s = h.spec
+    A, G, T = base_pos.shape[0], grid.shape[0], s.pred_len
+    if mc_ptr == 0:
+        raise RuntimeError("multicast pointer is null: the symmetric buffer has no NVSwitch multicast mapping")
+    rc = _lib.load().fc_grid_log_prob_multicast(
+        h.ptr, _chk(base_pos, (A, 2), "base_pos", h), _chk(cond, (A, T, s.cond_size), "cond", h),
+        _chk(cond_traj, (A, T, 2), "cond_traj", h), _chk(grid, (G, 2), "grid", h), None, seed, prefix_mode,
+        int(sequential), mc_ptr + 4 * offset_elems, sa, sp, st, A, G, precision, _stream(h))
+    h.check(rc, "fc_grid_log_prob_multicast")
+
+
 @torch.library.custom_op("flowchain::sample_with_log_prob", mutates_args=())
 def sample_with_log_prob(hid: int, base_pos: torch.Tensor, cond: torch.Tensor, S: int,
                          z0: Optional[torch.Tensor], eps: Optional[torch.Tensor], seed: int,

@@ -90,6 +90,17 @@ int fc_grid_log_prob(fc_handle* h, const float* base_pos, const float* cond, con
                      int K, float* out, int64_t out_agent_stride, int64_t out_point_stride,
                      int64_t out_step_stride, int64_t A, int64_t G, int precision, void* stream);
 
+/* Multi-GPU variant of fc_grid_log_prob (K = 1): `out_multicast` is the NVSwitch MULTICAST address of a symmetric
+ * buffer (cuMulticast* / torch symmetric memory), offset to this rank's block of the global (A_total, T, G) maps.
+ * The kernel's ordinary 4-byte result stores (system scope) are replicated to every peer by the switch, i.e. the
+ * all-gather that the reference-side wrapper would run after the density evaluation (one ncclAllGather)
+ * is performed by the stores themselves, tile by tile, with no second kernel.  The caller runs one cross-rank barrier
+ * before reading the maps.  Replaces: flow.log_prob over rows = A*G (fastpredNF.py:450-465) + the all-gather. */
+int fc_grid_log_prob_multicast(fc_handle* h, const float* base_pos, const float* cond, const float* cond_traj,
+                               const float* grid, const float* eps, uint64_t seed, int prefix_mode, int sequential,
+                               float* out_multicast, int64_t out_agent_stride, int64_t out_point_stride,
+                               int64_t out_step_stride, int64_t A, int64_t G, int precision, void* stream);
+
 /* Replaces: fastpredNF.sample_with_log_prob -> fastpredNF_separate_cond.inverse (fastpredNF.py:472-477,
  * 586-607).  base_pos (B,2), cond (B,T,C0) are per agent and expanded over the S samples on the fly
  * (the reference expands them, fastpredNF.py:106-108).  z0 (B*S,2)|NULL is the standard-normal base
