@@ -61,6 +61,41 @@ def ncu_traffic(precision: str):
     return tot
 
 
+def update_latency(flow, spec, dev, agents_list=(1, 64), S=10000, t=1, reps=1000):
+    """BASELINE.json's second metric: p50 latency of the rapid update (predict_from_new_obs, fastpredNF.py:142-164) on
+    caches produced by the sampler, launched from a captured CUDA graph, CUDA-event timed, `reps` replays."""
+    import torch
+    h = flow.engine()
+    res = {"samples": S, "t": t, "reps": reps, "launch": "cuda graph replay, CUDA events", "unit": "us"}
+    for A in agents_list:
+        inp = synth.make_inputs(spec, A, seed=3)
+        bp = torch.from_numpy(inp["base_pos"]).to(dev)
+        cd = torch.from_numpy(inp["cond"]).to(dev)
+        seq, lp, ldjs, base = torch.ops.flowchain.sample_with_log_prob(h.id, bp, cd, S, None, None, 7, 0)
+        prob0 = torch.cat([seq, lp[..., None]], dim=-1).contiguous()
+        norm = torch.ops.flowchain.base_normalizer(h.id, base.contiguous())
+        new_pos = (bp + 0.05).contiguous()
+        g = torch.cuda.CUDAGraph()
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            for _ in range(3):
+                torch.ops.flowchain.update(h.id, new_pos, t, prob0, ldjs, norm)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g, stream=st):
+                torch.ops.flowchain.update(h.id, new_pos, t, prob0, ldjs, norm)
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, b in evs:
+            a.record()
+            g.replay()
+            b.record()
+        torch.cuda.synchronize()
+        times = np.array([a.elapsed_time(b) for a, b in evs]) * 1e3
+        res[f"p50_{A}_agents"] = float(np.median(times))
+        res[f"p99_{A}_agents"] = float(np.quantile(times, 0.99))
+    return res
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -357,6 +392,8 @@ def run_ours(args):
                          "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
                          "kernel_ms": kern_ms, "algorithmic_flops_per_launch": flops_launch},
         }
+        if world == 1:
+            line["update_latency"] = update_latency(flow, spec, dev)
         if world == 1 and not args.no_cpu_baseline:
             rate, med, nrep = cpu_port_rate(spec, params, seconds=args.cpu_seconds)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": blas_threads(), "kind": "port",
