@@ -438,7 +438,6 @@ static int grid_log_prob_impl(fc_handle* h, const float* base_pos, const float* 
                               int K, float* out, int64_t out_agent_stride, int64_t out_point_stride,
                               int64_t out_step_stride, int64_t A, int64_t G, int precision, void* stream_, int multicast) {
     if (ready(h)) return 1;
-    if (multicast && K != 1) return fail(h, "multicast output supports K = 1 only");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (A < 0 || G < 0) return fail(h, "negative size");
     if (K < 1 || K > 4096) return fail(h, "K must be in [1, 4096], got %d", K);
@@ -456,7 +455,11 @@ static int grid_log_prob_impl(fc_handle* h, const float* base_pos, const float* 
     a.N = A * G * K; a.PPA = G * K; a.K = K;
     a.seq_klo = 0; a.seq_jlo = 0;
     a.out_sys = multicast ? 1 : 0;
-    if (K == 1) {
+    // K = 2^j <= 32: the K samples of a point are consecutive rows = consecutive lanes, and logsumexp_k - log K is reduced
+    // with warp shuffles inside the density kernel (one store per point and step); other K go through a scratch buffer
+    const bool fuse_k = K > 1 && K <= 32 && (K & (K - 1)) == 0;
+    if (K == 1 || fuse_k) {
+        a.fuse_k = fuse_k ? 1 : 0;
         a.out = out; a.out_sa = out_agent_stride; a.out_sp = out_point_stride; a.out_st = out_step_stride;
         return launch_density(h, a, sequential ? MODE_SEQUENTIAL : MODE_SEPARATE, precision, stream);
     }

@@ -441,10 +441,10 @@ k_separate_fp32(const StepPlan* __restrict__ plans, const float* __restrict__ wb
     load_y<R>(t, a, dm, step, step, false);
     __syncthreads();
     cif_step<R, false>(t, a, t.sp->eps_off, (unsigned)step);
-    if (r < R && row0 + r < a.N) {
+    if (r < R) {          // whole warps: store_result reduces K importance samples across lanes
         const float lp = normal_lp2(t.Z[r], t.Z[R + r], t.PREV[r], t.PREV[R + r], t.sp->std[0], t.sp->std[1]) + t.ACC[r];
         const long long n = row0 + r;
-        store_out(a, t.ROWA[r] * a.out_sa + (n % a.PPA) * a.out_sp + (long long)step * a.out_st, lp);
+        store_result(a, t.ROWA[r], n % a.PPA, step, lp, n < a.N);
     }
 }
 
@@ -478,12 +478,12 @@ k_sequential_fp32(const StepPlan* __restrict__ plans, const float* __restrict__ 
         cif_step<R, false>(t, a, col, (unsigned)(k * 64 + j + 4096));
     }
     __syncthreads();
-    if (r < R && row0 + r < a.N) {
+    if (r < R) {
         const float s0 = __ldg(&plans[0].std[0]), s1 = __ldg(&plans[0].std[1]);
         const float lp = normal_lp2(t.Z[r], t.Z[R + r], t.PREV[r], t.PREV[R + r], s0, s1) +
                          t.ACC[r] / (float)(j - a.seq_jlo + 1);
         const long long n = row0 + r;
-        store_out(a, t.ROWA[r] * a.out_sa + (n % a.PPA) * a.out_sp + (long long)(j - a.seq_jlo) * a.out_st, lp);
+        store_result(a, t.ROWA[r], n % a.PPA, j - a.seq_jlo, lp, n < a.N);
     }
 }
 

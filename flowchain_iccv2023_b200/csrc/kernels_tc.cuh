@@ -756,9 +756,9 @@ k_separate_tc(const TcStep* __restrict__ steps, const uint8_t* __restrict__ img,
                 layer_end(x);
             }
         }
-        if (valid) {
+        {     // whole warps (row = thread): store_result reduces K importance samples across lanes
             const float lp = normal_lp2(z0, z1, prev0, prev1, ts.std[0], ts.std[1]) + lacc;
-            store_out(a, ag * a.out_sa + rem * a.out_sp + (long long)step * a.out_st, lp);
+            store_result(a, ag, rem, step, lp, valid);
         }
     }
 

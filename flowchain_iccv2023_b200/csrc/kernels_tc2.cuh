@@ -777,9 +777,9 @@ k_separate_tc2(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
             }
         }
         T2_TICK(10)  // tail
-        if (valid && x.part == 0) {
+        if (x.part == 0) {      // whole warps: store_result reduces K importance samples across lanes
             const float lp = normal_lp2(z0, z1, prev0, prev1, ts.std[0], ts.std[1]) + lacc;
-            store_out(a, ag * a.out_sa + rem * a.out_sp + (long long)step * a.out_st, lp);
+            store_result(a, ag, rem, step, lp, valid);
         }
     }
 

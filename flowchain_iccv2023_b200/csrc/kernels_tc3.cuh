@@ -620,13 +620,13 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
             }
         }
     T3_STEP_END
-        if (!INV && valid && x.part == 0) {
+        if (!INV && x.part == 0) {      // whole warps: store_result reduces K importance samples across lanes
             if (MODE == 0) {
                 const float lp = normal_lp2(z0, z1, prev0, prev1, m.cur->std[0], m.cur->std[1]) + lacc;
-                store_out(a, ag * a.out_sa + rem * a.out_sp + (long long)jstep * a.out_st, lp);
+                store_result(a, ag, rem, jstep, lp, valid);
             } else {      // base = Normal(base_pos, std[0]); ldj = mean over the chain steps of this result index
                 const float lp = normal_lp2(z0, z1, prev0, prev1, __ldg(&steps[0].std[0]), __ldg(&steps[0].std[1])) + lacc / (float)(jstep - dm.jlo + 1);
-                store_out(a, ag * a.out_sa + rem * a.out_sp + (long long)(jstep - dm.jlo) * a.out_st, lp);
+                store_result(a, ag, rem, jstep - dm.jlo, lp, valid);
             }
         }
     T3_ITEM_END

@@ -66,6 +66,8 @@ struct RowArgs {
     long long out_sa, out_sp, out_st;
     int seq_klo;           // sequential: lowest chain step applied (0, or T - n_step)
     int seq_jlo;           // sequential: first result index written (0, or T - n_step - 1)
+    int fuse_k;            // 1: K = 2^j <= 32 importance samples of a point sit in consecutive rows (= lanes): logsumexp_k - log K
+                           // is reduced with warp shuffles in registers and ONE value per (point, step) is stored
     int out_sys;           // 1: `out` is an NVSwitch multicast address of a symmetric buffer: every store is replicated to
                            // all peers, so the density maps are all-gathered by the stores themselves (system-scope stores)
 };
@@ -75,6 +77,23 @@ struct RowArgs {
 __device__ __forceinline__ void store_out(const RowArgs& a, long long idx, float v) {
     if (a.out_sys) asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(a.out + idx), "f"(v) : "memory");
     else a.out[idx] = v;
+}
+// Result of row (agent ag, point-row rem = n % PPA) at output step `tidx`.  Must be reached by all 32 lanes of the warp
+// (rows are consecutive lanes; `valid` masks rows past N).  K > 1 fused: CIF importance-sample bound
+// log p ~= logsumexp_k lp_k - log K, rows ordered (a, g, k).
+__device__ __forceinline__ void store_result(const RowArgs& a, long long ag, long long rem, long long tidx, float lp, bool valid) {
+    if (a.fuse_k) {
+        float m = valid ? lp : -INFINITY;
+        for (int o = 1; o < a.K; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float s = (valid && m != -INFINITY) ? expf(lp - m) : 0.0f;
+        for (int o = 1; o < a.K; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (valid && (rem % a.K) == 0) {
+            const float v = (m == -INFINITY) ? -INFINITY : m + logf(s) - logf((float)a.K);
+            store_out(a, ag * a.out_sa + (rem / a.K) * a.out_sp + tidx * a.out_st, v);
+        }
+    } else if (valid) {
+        store_out(a, ag * a.out_sa + rem * a.out_sp + tidx * a.out_st, lp);
+    }
 }
 #endif
 

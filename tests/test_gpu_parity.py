@@ -175,10 +175,12 @@ def test_full_lattice_config1(flows):
     assert_close32(out, ref, "config1 shared")
 
 
-def test_importance_samples(flows):
-    """Extension D1: K importance samples; K = 1 is the reference, K > 1 = logsumexp_k - log K."""
+@pytest.mark.parametrize("K", [3, 4, 32])
+def test_importance_samples(flows, K):
+    """Extension D1: K importance samples; K = 1 is the reference, K > 1 = logsumexp_k - log K.  K = 2^j <= 32 is
+    reduced with warp shuffles inside the density kernel, other K through a scratch buffer + k_logsumexp_k."""
     f, spec, p, g = flows("odd_small")
-    A, G, K = 3, 7, 4
+    A, G = 3, 7
     inp = synth.make_inputs(spec, A, seed=40)
     grid = synth.make_grid(3)[:G]
     eps = synth.make_eps(spec, A * G * K, 41)
@@ -186,7 +188,7 @@ def test_importance_samples(flows):
     e = eps.reshape(A * G, K, -1).transpose(1, 0, 2)
     ref = orc.log_prob_importance(p, bp, x, cd, e, np.float64).reshape(A, G, -1)
     out = f.grid_log_prob(T(inp["base_pos"]), T(inp["cond"]), T(grid), K=K, eps=T(eps)).cpu().numpy()
-    assert_close32(out, ref, "K=4 importance")
+    assert_close32(out, ref, f"K={K} importance")
 
 
 def test_philox_mode_is_seeded_and_plausible(flows):

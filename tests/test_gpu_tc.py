@@ -169,6 +169,24 @@ def test_tc_grid_golden(flow_default, mode):
     check("grid shared", out.transpose(0, 2, 1), g["grid_shared_64"], mode)
 
 
+@pytest.mark.parametrize("K", [4, 5])
+def test_tc_importance_samples(flow_default, K):
+    """K importance samples on the tensor-core path (fused warp-shuffle logsumexp for K = 4, scratch path for K = 5)."""
+    f, spec, p, g = flow_default
+    A, G = 2, 37
+    inp = synth.make_inputs(spec, A, seed=50)
+    grid = synth.make_grid(7)[:G]
+    eps = synth.make_eps(spec, A * G * K, 51)
+    bp, x, cd = orc.grid_rows(inp["base_pos"], inp["cond"], grid)
+    e = eps.reshape(A * G, K, -1).transpose(1, 0, 2)
+    ref = orc.log_prob_importance(p, bp, x, cd, e, np.float64).reshape(A, G, -1)
+    out = f.grid_log_prob(T(inp["base_pos"]), T(inp["cond"]), T(grid), K=K, eps=T(eps), precision=_lib.FC_PREC_F16X3).cpu().numpy()
+    check(f"K={K} importance", out, ref, "f16x3")
+    maps = f.grid_log_prob(T(inp["base_pos"]), T(inp["cond"]), T(grid), K=K, eps=T(eps), precision=_lib.FC_PREC_F16X3,
+                           map_layout=True).cpu().numpy()
+    np.testing.assert_array_equal(maps, out.transpose(0, 2, 1))
+
+
 @pytest.mark.parametrize("mode", list(MODES))
 def test_tc_ragged_rows_vs_oracle(flow_default, mode):
     f, spec, p, g = flow_default
