@@ -247,3 +247,33 @@ def test_config2_full_size_properties(flow_default):
     assert frac >= 0.9999 and worst < 3.0                            # fp32 itself is up to 3e-6 |ref| off
     rows = f.grid_log_prob(bp[:2], cd[:2], grid, seed=42, precision=_lib.FC_PREC_F16X3)          # (2, G, T) row order
     assert torch.equal(rows.transpose(1, 2), m1[:2])                 # same rows, same streams, other layout
+
+
+def test_tc_deep_blocks_golden():
+    """Config-5 depth knob (6 coupling blocks per CIF step, pred_len 4) on the tensor-core kernel: per-step density, chain
+    and sampler against the golden tape; and a shape the tensor-core path does not cover fails loudly."""
+    from flowchain_iccv2023_b200.flow import fastpredNF_CIF_separate_cond
+    spec, p, g = load_golden("deep_blocks")
+    f = fastpredNF_CIF_separate_cond(2, spec.n_blocks, spec.hidden_size, spec.n_hidden, spec.cond_size,
+                                     flow_architecture="realNVP", pred_len=spec.pred_len)
+    f.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()}, strict=True)
+    f = f.cuda().eval()
+    P = _lib.FC_PREC_F16X3
+    out = f.log_prob(T(g["base_pos"]), T(g["x"]), T(g["cond"]), eps=T(g["eps"]), precision=P).cpu().numpy()
+    check("deep log_prob", out, g["log_prob_64"], "f16x3")
+    out = f.log_prob_sequential(T(g["base_pos"]), T(g["x"]), T(g["cond"]), eps=T(g["eps_seq"]), precision=P).cpu().numpy()
+    check("deep log_prob_sequential", out, g["log_prob_seq_64"], "f16x3")
+    B, S, D = g["z0"].shape
+    bp = T(g["base_pos"][:B])[:, None].expand(-1, S, -1)
+    cd = T(g["cond"][:B])[:, None].expand(-1, S, -1, -1)
+    seq, lp, ldjs, base = f.sample_with_log_prob(bp, cd, z0=T(g["z0"]), eps=T(g["eps_sample"]), precision=P)
+    assert np.abs(seq.cpu().numpy() - g["sample_seq_64"]).max() <= 2e-4
+    np.testing.assert_allclose(lp.cpu().numpy(), g["sample_log_prob_64"], atol=5e-3, rtol=1e-4)
+
+    spec2, p2, g2 = load_golden("odd_small")                  # hidden 40: not a multiple of 16
+    f2 = fastpredNF_CIF_separate_cond(2, spec2.n_blocks, spec2.hidden_size, spec2.n_hidden, spec2.cond_size,
+                                      flow_architecture="realNVP", pred_len=spec2.pred_len)
+    f2.load_state_dict({k: torch.from_numpy(v) for k, v in p2.items()}, strict=True)
+    f2 = f2.cuda().eval()
+    with pytest.raises(RuntimeError, match="FC_PREC_FP32"):
+        f2.log_prob(T(g2["base_pos"]), T(g2["x"]), T(g2["cond"]), eps=T(g2["eps"]), precision=P)
