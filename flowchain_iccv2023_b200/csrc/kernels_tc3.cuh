@@ -19,7 +19,8 @@ constexpr uint32_t kT3Acc0 = 0, kT3Acc1 = 80;            // fp32 accumulators of
 constexpr uint32_t kT3InHi = 160, kT3InLo = 184;         // [z|w, cond, prefix] operand, K <= 48
 constexpr uint32_t kT3UHi = 208, kT3ULo = 232;           // [u, mx] operand, K <= 48
 constexpr uint32_t kT3TileCols = 256;
-constexpr int kT3Threads = 16 * 32 + 96;                  // 2 x 8 compute warps, producer, 2 issuers
+constexpr int kT3Threads = 16 * 32 + 128;                 // 2 x 8 compute warps + a service warpgroup (producer, 2 issuers, 1 idle)
+constexpr int kT3ComputeRegs = 104, kT3ServiceRegs = 56;   // setmaxnreg split of the register file (see the kernel)
 constexpr int kT3OnesOff = 12288;                         // constant [128 x 16] fp16 tile, columns 0..2 = 1 (bias fold)
 constexpr int kT3Header = 16384;                          // barriers, step table, row-partial buffers, bias ring, ones tile
 constexpr int kT3BiasEntry = 768;                         // bytes per (net, job & 3) entry of the bias ring
@@ -233,6 +234,17 @@ __device__ __forceinline__ int t3_chunk_of_job(const T2Step& ts, int ci, bool in
     if (ci < 6) return nb6 + ci;
     if (ci < nb6) { const int bi = (ci - 6) / L2; return 6 + (ts.n_blocks - 1 - bi) * L2 + (ci - 6 - bi * L2); }
     return ci - nb6;
+}
+
+// ===== fourth warp of the service warpgroup: only takes part in the CTA-wide step-table reloads =====
+__device__ __forceinline__ void t3_idle(const T2Step* __restrict__ steps, const T3Dims& dm, long long pairs_per_step, long long total_items,
+                                        uint8_t* smem) {
+    const T3Smem m = t3_smem(smem, dm);
+    T3_ITEM_BEGIN(dm.seq)
+    T3_STEP_BEGIN(dm.seq)
+        (void)ts;
+    T3_STEP_END
+    T3_ITEM_END
 }
 
 // ===== weight producer (one warp): streams the step's chunks through the ring =====
@@ -676,9 +688,18 @@ k_separate_tc3(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tslot);
 
     // three roles (inlined: separate noinline role functions measured 3 ms slower)
-    if (warp < 16) t3_compute<NPASS, FOLD_D, FOLD_C, MODE>(steps, a, o, dm, pairs_per_step, total_items, smem, tmem_base);
-    else if (warp == 16) t3_producer(steps, img, dm, pairs_per_step, total_items, smem);
-    else t3_issuer<NPASS>(steps, dm, pairs_per_step, total_items, smem, tmem_base, warp - 17);
+    // Warp-specialised register split (setmaxnreg, per warpgroup): the kernel launches with 96 registers per thread
+    // (640 threads); the service warpgroup (warps 16-19) gives back all but 56, the four epilogue warpgroups grow to 104.
+    // setmaxnreg.inc only draws on what .dec released: 4 x 128 x (104 - 96) = 4096 <= 128 x (96 - 56) = 5120.
+    if (warp < 16) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kT3ComputeRegs));
+        t3_compute<NPASS, FOLD_D, FOLD_C, MODE>(steps, a, o, dm, pairs_per_step, total_items, smem, tmem_base);
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kT3ServiceRegs));
+        if (warp == 16) t3_producer(steps, img, dm, pairs_per_step, total_items, smem);
+        else if (warp < 19) t3_issuer<NPASS>(steps, dm, pairs_per_step, total_items, smem, tmem_base, warp - 17);
+        else t3_idle(steps, dm, pairs_per_step, total_items, smem);
+    }
 
     tc_fence_before();
     __syncthreads();
