@@ -335,6 +335,10 @@ def run_ours(args):
 
     # ---- end-to-end leg: public API with HOST buffers, H2D + D2H inside the timed region -----------------
     def e2e_step():
+        if world == 1:      # public host-output API: 4 agent chunks, device->host copy of a chunk overlaps the next chunk
+            seed[0] += 1
+            flow.grid_log_prob_to_host(h_base, h_cond, h_grid, out=h_out, chunks=4, seed=seed[0])
+            return
         b = h_base.to(dev, non_blocking=True)
         c = h_cond.to(dev, non_blocking=True)
         g = h_grid.to(dev, non_blocking=True)
@@ -345,8 +349,7 @@ def run_ours(args):
             return
         seed[0] += 1
         maps = flow.grid_log_prob(b, c, g, seed=seed[0], map_layout=True)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, maps)
+        dist.all_gather_into_tensor(gathered, maps)
         h_out.copy_(maps, non_blocking=True)
     for _ in range(2):
         e2e_step()

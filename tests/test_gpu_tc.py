@@ -277,3 +277,21 @@ def test_tc_deep_blocks_golden():
     f2 = f2.cuda().eval()
     with pytest.raises(RuntimeError, match="FC_PREC_FP32"):
         f2.log_prob(T(g2["base_pos"]), T(g2["x"]), T(g2["cond"]), eps=T(g2["eps"]), precision=P)
+
+
+def test_grid_log_prob_to_host_overlapped(flow_default):
+    """Host-output API (chunked evaluation with the device->host copy on a side stream): chunk i equals a direct call on
+    its agents with seed + i, and the pinned result is complete once the current stream is synchronised."""
+    f, spec, p, g = flow_default
+    A = 6
+    inp = synth.make_inputs(spec, A, seed=77)
+    grid = synth.make_grid(33)
+    hb, hc, hg = (torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (inp["base_pos"], inp["cond"], grid))
+    out = f.grid_log_prob_to_host(hb, hc, hg, chunks=3, seed=100, precision=_lib.FC_PREC_F16X3)
+    torch.cuda.current_stream().synchronize()
+    assert out.shape == (A, spec.pred_len, grid.shape[0]) and out.is_pinned()
+    for i in range(3):
+        lo, hi = 2 * i, 2 * i + 2
+        ref = f.grid_log_prob(T(inp["base_pos"][lo:hi]), T(inp["cond"][lo:hi]), T(grid), seed=100 + i, map_layout=True,
+                              precision=_lib.FC_PREC_F16X3).cpu()
+        assert torch.equal(out[lo:hi], ref)
