@@ -35,6 +35,7 @@ struct T3Dims {
                                 // 2: sampler (flow.sample_with_log_prob): item = tiles, inverse steps 0 .. T-1
     int32_t klo, jlo;           // chain mode: lowest chain step applied, first result index written
     int32_t no_fold;            // 1: ignore the chunks' bias tiles (launches whose steps mix folded and plain widths)
+    int32_t single;             // 1: one tile per item (group 1 idles): small launches that would leave SMs empty otherwise
 };
 
 namespace t3 {
@@ -284,6 +285,7 @@ __device__ __forceinline__ void t3_issuer(const T2Step* __restrict__ steps, cons
     const int lane = threadIdx.x & 31;
     uint32_t ring_it = 0;
     uint32_t opnd_c0 = 0, opnd_c1 = 0, fin_c0 = 0, fin_c1 = 0;    // per-tile phase counters
+    const int ntile = dm.single ? 1 : 2;
     T3_ITEM_BEGIN(dm.seq)
     T3_STEP_BEGIN(dm.seq)
         const uint32_t base = ring_it;
@@ -315,7 +317,7 @@ __device__ __forceinline__ void t3_issuer(const T2Step* __restrict__ steps, cons
             uint32_t leader;
             asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(leader));
 #pragma unroll 1
-            for (int t = 0; t < 2; ++t) {
+            for (int t = 0; t < ntile; ++t) {
                 const uint32_t tb0 = tmem_base + (uint32_t)t * kT3TileCols;
                 const uint32_t acc = tb0 + (net ? kT3Acc1 : kT3Acc0);
                 const uint32_t ta_hi = tb0 + (src == 0 ? kT3InHi : kT3UHi), ta_lo = tb0 + (src == 0 ? kT3InLo : kT3ULo);
@@ -352,14 +354,14 @@ __device__ __forceinline__ void t3_issuer(const T2Step* __restrict__ steps, cons
                         }
                     }
                     umma_commit(&bars->mma_done[t][net]);
-                    if (t == 1) umma_commit(&bars->empty[it & smask]);   // both tiles' MMAs done -> slot free
+                    if (t == ntile - 1) umma_commit(&bars->empty[it & smask]);   // all tiles' MMAs done -> slot free
                 }
                 __syncwarp();
             }
         }
         // consume the final `fin` phase of both tiles (the q-density epilogues) to stay in step with the groups
         mbar_wait(&bars->fin[0], fin_c0 & 1u); fin_c0++;
-        mbar_wait(&bars->fin[1], fin_c1 & 1u); fin_c1++;
+        if (ntile == 2) { mbar_wait(&bars->fin[1], fin_c1 & 1u); fin_c1++; }
         ring_it += (uint32_t)ts.nchunks;
     T3_STEP_END
     T3_ITEM_END
@@ -389,9 +391,17 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
     x.bias_ring = smem_u32(bias_ring);
     x.h_stride = h_stride;
     x.h_base = smem_u32(m.hbuf) + (uint32_t)x.g * 4u * h_stride;
+    if (dm.single && x.g == 1) {      // one tile per item: the second group only takes part in the step-table reloads
+        T3_ITEM_BEGIN(MODE)
+        T3_STEP_BEGIN(MODE)
+            (void)ts;
+        T3_STEP_END
+        T3_ITEM_END
+        return;
+    }
     T3_ITEM_BEGIN(MODE)
         const int g = x.g;
-        long long n = (pair * 2 + g) * 128 + x.row;
+        long long n = (dm.single ? pair : pair * 2 + g) * 128 + x.row;
         const bool valid = n < a.N;
         if (!valid) n = a.N - 1;
         const long long ag = n / a.PPA, rem = n % a.PPA, pt = rem / a.K;
@@ -714,7 +724,10 @@ inline int tc3_launch_separate(const T2Dims& dm2, const std::vector<T2Step>& hst
                                const RowArgs& a, int num_sms, int smem_optin, cudaStream_t stream, uint64_t* launches, std::string* msg) {
     if (!dm2.supported || d_img == nullptr) { *msg = "the tensor-core path does not support this model shape; use FC_PREC_FP32"; return 1; }
     const int T = dm2.T;
-    const long long tiles = (a.N + 127) / 128, pairs = (tiles + 1) / 2;
+    const long long tiles = (a.N + 127) / 128;
+    // small launches (fewer tile pairs x steps than SMs) run one tile per item so that twice as many SMs work
+    const bool single = ((tiles + 1) / 2) * T < num_sms;
+    const long long pairs = single ? tiles : (tiles + 1) / 2;
     int lo = 0;
     while (lo < T) {
         // group consecutive steps with the same operand-width class
@@ -729,7 +742,7 @@ inline int tc3_launch_separate(const T2Dims& dm2, const std::vector<T2Step>& hst
             for (int ci = 0; ci < hsteps[s].nchunks; ++ci) slot = hsteps[s].chunk_bytes[ci] > slot ? hsteps[s].chunk_bytes[ci] : slot;
         slot = (slot + 127) / 128 * 128;
         T3Dims dm{};
-        dm.slot_bytes = slot; dm.Wmax = wc; dm.T = T; dm.C0 = dm2.C0; dm.step_lo = lo; dm.step_hi = hi;
+        dm.slot_bytes = slot; dm.Wmax = wc; dm.T = T; dm.C0 = dm2.C0; dm.step_lo = lo; dm.step_hi = hi; dm.single = single ? 1 : 0;
         const size_t fixed = (size_t)kT3Header + (size_t)8 * 128 * wc * 2;
         // a weight slot is handed back by the tcgen05.commit of the MMAs that read it, so 2 slots (one per net) already
         // pipeline; 4 when they fit
@@ -769,7 +782,9 @@ inline int tc3_launch_sequential(const T2Dims& dm2, const std::vector<T2Step>& h
                                  const RowArgs& a, int num_sms, int smem_optin, cudaStream_t stream, uint64_t* launches, std::string* msg) {
     if (!dm2.supported || d_img == nullptr) { *msg = "the tensor-core path does not support this model shape; use FC_PREC_FP32"; return 1; }
     const int T = dm2.T;
-    const long long tiles = (a.N + 127) / 128, pairs = (tiles + 1) / 2;
+    const long long tiles = (a.N + 127) / 128;
+    const bool single = ((tiles + 1) / 2) * (T - a.seq_jlo) < num_sms;
+    const long long pairs = single ? tiles : (tiles + 1) / 2;
     int wc = 64, slot = 0;
     for (int s = 0; s < T; ++s) {
         const int w = hsteps[s].Wd > hsteps[s].Hc ? hsteps[s].Wd : hsteps[s].Hc;
@@ -779,7 +794,7 @@ inline int tc3_launch_sequential(const T2Dims& dm2, const std::vector<T2Step>& h
     slot = (slot + 127) / 128 * 128;
     T3Dims dm{};
     dm.slot_bytes = slot; dm.Wmax = wc; dm.T = T; dm.C0 = dm2.C0; dm.step_lo = a.seq_jlo; dm.step_hi = T - 1;
-    dm.seq = 1; dm.klo = a.seq_klo; dm.jlo = a.seq_jlo; dm.no_fold = 1;
+    dm.seq = 1; dm.klo = a.seq_klo; dm.jlo = a.seq_jlo; dm.no_fold = 1; dm.single = single ? 1 : 0;
     const size_t fixed = (size_t)kT3Header + (size_t)8 * 128 * wc * 2;
     dm.nslots_log2 = (fixed + (size_t)4 * slot <= (size_t)smem_optin) ? 2 : 1;
     const size_t smem = fixed + ((size_t)1 << dm.nslots_log2) * slot;
@@ -803,7 +818,9 @@ inline int tc3_launch_sample(const T2Dims& dm2, const std::vector<T2Step>& hstep
                              std::string* msg) {
     if (!dm2.supported || d_img == nullptr) { *msg = "the tensor-core path does not support this model shape; use FC_PREC_FP32"; return 1; }
     const int T = dm2.T;
-    const long long tiles = (a.N + 127) / 128, pairs = (tiles + 1) / 2;
+    const long long tiles = (a.N + 127) / 128;
+    const bool single = (tiles + 1) / 2 < num_sms;
+    const long long pairs = single ? tiles : (tiles + 1) / 2;
     int wc = 64, slot = 0;
     for (int s = 0; s < T; ++s) {
         const int w = hsteps[s].Wd > hsteps[s].Hc ? hsteps[s].Wd : hsteps[s].Hc;
@@ -813,7 +830,7 @@ inline int tc3_launch_sample(const T2Dims& dm2, const std::vector<T2Step>& hstep
     slot = (slot + 127) / 128 * 128;
     T3Dims dm{};
     dm.slot_bytes = slot; dm.Wmax = wc; dm.T = T; dm.C0 = dm2.C0; dm.step_lo = 0; dm.step_hi = T - 1;
-    dm.seq = 2; dm.no_fold = 1;
+    dm.seq = 2; dm.no_fold = 1; dm.single = single ? 1 : 0;
     const size_t fixed = (size_t)kT3Header + (size_t)8 * 128 * wc * 2;
     dm.nslots_log2 = (fixed + (size_t)4 * slot <= (size_t)smem_optin) ? 2 : 1;
     const size_t smem = fixed + ((size_t)1 << dm.nslots_log2) * slot;
