@@ -48,6 +48,10 @@ enum { FC_PREC_FP32 = 0,    /* CUDA-core fp32, parity 1e-4 (+rel) nats          
        FC_PREC_F16X3 = 2,   /* tcgen05, split-fp16 operands (a_hi+a_lo)(W_hi+W_lo), 3 MMA passes, fp32 accumulate:
                                fp32-grade, meets the 5e-3 nats tensor-core parity bar                             */
        FC_PREC_F16 = 3 };   /* tcgen05, fp16 operands / fp32 accumulate, single pass: ~3e-2 nats                  */
+/* Coverage: FC_PREC_FP32 every entry point and model shape.  FC_PREC_F16X3 / FC_PREC_F16: fc_log_prob,
+ * fc_log_prob_sequential, fc_grid_log_prob[_multicast] (per-step and chain) and fc_sample_with_log_prob, for
+ * hidden_size % 16 == 0, hidden_size <= 96 (chain / sampler <= 80) and 2*(cond_size + 2*pred_len) <= 96; other shapes
+ * return an error that names FC_PREC_FP32.  FC_PREC_BF16: per-step density only. */
 
 /* prefix modes of the dense-grid evaluation */
 enum { FC_PREFIX_SELF = 0,     /* x[:, i] = g for every step (the literal reference call)   */
@@ -105,7 +109,8 @@ int fc_grid_log_prob_multicast(fc_handle* h, const float* base_pos, const float*
  * 586-607).  base_pos (B,2), cond (B,T,C0) are per agent and expanded over the S samples on the fly
  * (the reference expands them, fastpredNF.py:106-108).  z0 (B*S,2)|NULL is the standard-normal base
  * draw (u0 = base_pos + std0*z0), eps (B*S,E)|NULL.
- * Outputs: seq (B,S,T,2), log_prob (B,S,T), ldjs (B,S,T), base_lp (B,S). */
+ * Outputs: seq (B,S,T,2), log_prob (B,S,T), ldjs (B,S,T), base_lp (B,S).
+ * precision: FC_PREC_FP32 (CUDA cores) or FC_PREC_F16X3 / FC_PREC_F16 (the tensor-core kernel run in the inverse direction). */
 int fc_sample_with_log_prob(fc_handle* h, const float* base_pos, const float* cond, const float* z0,
                             const float* eps, uint64_t seed, float* seq, float* log_prob, float* ldjs,
                             float* base_lp, int64_t B, int64_t S, int precision, void* stream);
