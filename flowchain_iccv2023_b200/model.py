@@ -115,6 +115,14 @@ class fastpredNF_TP(nn.Module):
         data_dict[("prob_st", 0)] = torch.cat([seq, lp[..., None]], dim=-1)
         return data_dict
 
+    def gt_log_prob(self, data_dict: Dict, **kw) -> torch.Tensor:
+        """Exact log p of the ground-truth future under the per-step density: flow.log_prob(base_pos, gt_st, cond) -> (B, T).
+        Replaces the visualiser's detour of interpolating a KDE of samples on a grid and reading it off at the GT
+        (src/visualization/TP_visualizer.py:165-179): the density is analytic, so it is evaluated."""
+        dist_args = self.encoder(data_dict)
+        base_pos = self.get_base_pos(data_dict)
+        return self.flow.log_prob(base_pos, data_dict["gt_st"], dist_args, **kw)
+
     def update(self, data_dict: Dict) -> Dict:
         raise NotImplementedError(
             "fastpredNF_TP.update is the Adam training step (fastpredNF.py:186-202); training stays on the "

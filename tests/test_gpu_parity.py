@@ -227,3 +227,31 @@ def test_repack_after_in_place_update(flows):
         f.var.div_(1.5)
     c = f.log_prob(*args, eps=T(g["eps"]))
     assert not torch.allclose(a, b) and torch.allclose(a, c, atol=1e-4)
+
+
+def test_wrapper_grid_and_gt_log_prob(flows):
+    """Density-map side of the wrapper: predict_forward (the reference's dead grid evaluation, working) and the exact
+    log p(gt) that replaces the visualiser's KDE + interpolation look-up, against the oracle on an injected tape."""
+    from flowchain_iccv2023_b200.model import fastpredNF_TP
+    f, spec, p, g = flows("default_eth")
+    B, Tn = 3, spec.pred_len
+    m = fastpredNF_TP(encoder=lambda d: T(g["cond"][:B]), pred_len=Tn, n_blocks=spec.n_blocks, n_hidden=spec.n_hidden,
+                      hidden_size=spec.hidden_size, cond_size=spec.cond_size)
+    m.flow = f
+    obs_st = torch.zeros(B, 8, 6, device="cuda")
+    obs_st[:, -1, 2:4] = T(g["base_pos"][:B])
+    gt = (g["base_pos"][:B, None, :] + 0.2 * synth.normal(91, "gt", (B, Tn, 2))).astype(np.float32)
+    eps = synth.make_eps(spec, B, 92)
+    out = m.gt_log_prob({"obs_st": obs_st, "gt_st": T(gt)}, eps=T(eps)).cpu().numpy()
+    ref = orc.log_prob(p, g["base_pos"][:B], gt, g["cond"][:B], eps, np.float64)
+    assert_close32(out, ref, "gt_log_prob")
+    n = 9
+    eps_g = synth.make_eps(spec, B * n * n, 93)
+    dd = m.predict_forward({"obs_st": obs_st}, sample_num_per_dim=n, eps=T(eps_g))
+    ps = dd[("prob_st", 0)].cpu().numpy()
+    assert ps.shape == (B, n * n, Tn, 3)
+    ax = np.linspace(-3.0, 3.0, n, dtype=np.float32)
+    grid = np.stack(np.meshgrid(ax, ax, indexing="ij"), -1).reshape(-1, 2)
+    np.testing.assert_allclose(ps[0, :, 0, :2], grid, atol=1e-6)
+    ref = orc.grid_log_prob_self(p, g["base_pos"][:B], g["cond"][:B], grid, eps_g, np.float64)
+    assert_close32(ps[..., 2], ref, "predict_forward")
