@@ -112,7 +112,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.lines, self.proc = index, [], None
+        self.index, self.lines, self.proc, self.begin = index, [], None, 0
+
+    def mark_begin(self):
+        """The timed region starts here: nvidia-smi was launched earlier (its start-up takes longer than a short timed
+        region), only the samples that arrive from now on are used."""
+        self.begin = len(self.lines)
 
     def start(self):
         try:
@@ -138,7 +143,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        window = "timed region"
+        lines = self.lines[self.begin:]
+        if not lines:                      # region shorter than one sampling period: same load ran during the warm-up
+            lines, window = self.lines, "warm-up + timed region"
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -151,7 +160,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def cpu_port_rate(spec, params, seconds: float, agents: int = 1, grid_n: int = 100):
@@ -297,13 +306,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)          # nvidia-smi starts now; only samples taken after mark_begin() count
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
 
     # ---- kernel-only leg: inputs resident in HBM, CUDA events on the launching (current) stream ----------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark_begin()
     l0 = handle.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
            torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
