@@ -594,6 +594,15 @@ extern "C" int fc_debug_t2prof(unsigned long long* out16, int reset) {
     return 0;
 }
 
+extern "C" int fc_debug_t3trace(unsigned long long* out, int reset) {   // 20 x 1024 entries, (tag << 48) | clock (needs -DFC_T3_TRACE=1)
+    if (out && cudaMemcpyFromSymbol(out, fc::g_t3trace, sizeof(unsigned long long) * 20 * 1024) != cudaSuccess) return 1;
+    if (reset) {
+        static unsigned long long z[20 * 1024];
+        if (cudaMemcpyToSymbol(fc::g_t3trace, z, sizeof z) != cudaSuccess) return 1;
+    }
+    return 0;
+}
+
 extern "C" int fc_debug_t2trace(unsigned long long* out, int reset) {   // 12 x 256 entries, (tag << 48) | clock
     if (out && cudaMemcpyFromSymbol(out, fc::g_t2trace, sizeof(unsigned long long) * 12 * 256) != cudaSuccess) return 1;
     if (reset) {

@@ -38,6 +38,18 @@ struct T3Dims {
     int32_t single;             // 1: one tile per item (group 1 idles): small launches that would leave SMs empty otherwise
 };
 
+// development aid (-DFC_T3_TRACE=1): lane 0 of every warp of CTA 0 logs (tag << 48 | clock) events of one launch
+#ifndef FC_T3_TRACE
+#define FC_T3_TRACE 0
+#endif
+__device__ unsigned long long g_t3trace[20][1024];
+#define T3_TR(tag)                                                                                                      \
+    if (FC_T3_TRACE && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && trace_n < 1024) {                                 \
+        long long now_;                                                                                                 \
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(now_));                                                            \
+        g_t3trace[threadIdx.x >> 5][trace_n++] = ((unsigned long long)(tag) << 48) | ((unsigned long long)now_ & 0xFFFFFFFFFFFFull); \
+    }
+
 namespace t3 {
 using namespace tc;
 using namespace t2;
@@ -257,12 +269,15 @@ __device__ __forceinline__ void t3_producer(const T2Step* __restrict__ steps, co
     const uint32_t smask = m.smask;
     const int lane = threadIdx.x & 31;
     uint32_t ring_it = 0;
+    int trace_n = 0; (void)trace_n;
     T3_ITEM_BEGIN(dm.seq)
     T3_STEP_BEGIN(dm.seq)
         for (int ci = 0; ci < ts.nchunks; ++ci, ++ring_it) {
             if (lane == 0) {
                 const uint32_t slot = ring_it & smask;
+                T3_TR(0x50 + (ci & 1))      // producer: wants a slot for chunk ci
                 mbar_wait(&bars->empty[slot], ((ring_it >> dm.nslots_log2) & 1u) ^ 1u);
+                T3_TR(0x52 + (ci & 1))      // slot free: bulk copy issued
                 const int pc = t3_chunk_of_job(ts, ci, dm.seq == 2);
                 mbar_expect_tx(&bars->full[slot], (uint32_t)ts.chunk_bytes[pc]);
                 bulk_load(slots + (size_t)slot * dm.slot_bytes, img + ts.chunk_off[pc], (uint32_t)ts.chunk_bytes[pc], &bars->full[slot]);
@@ -285,6 +300,7 @@ __device__ __forceinline__ void t3_issuer(const T2Step* __restrict__ steps, cons
     const int lane = threadIdx.x & 31;
     uint32_t ring_it = 0;
     uint32_t opnd_c0 = 0, opnd_c1 = 0, fin_c0 = 0, fin_c1 = 0;    // per-tile phase counters
+    int trace_n = 0; (void)trace_n;
     const int ntile = dm.single ? 1 : 2;
     T3_ITEM_BEGIN(dm.seq)
     T3_STEP_BEGIN(dm.seq)
@@ -293,6 +309,7 @@ __device__ __forceinline__ void t3_issuer(const T2Step* __restrict__ steps, cons
         for (int ci = net; ci < ts.nchunks; ci += 2) {
             const uint32_t it = base + (uint32_t)ci;
             mbar_wait(&bars->full[it & smask], (it >> dm.nslots_log2) & 1u);
+            T3_TR(0x20)              // weight chunk landed
             const int w = ts.job_wait[ci], src = ts.job_src[ci], Kp = ts.job_kp[ci], N = ts.job_n[ci];
             const bool has_bias_tile = ts.job_fold[ci] != 0, fold = has_bias_tile && !dm.no_fold;
             const int chunk_bytes = ts.chunk_bytes[t3_chunk_of_job(ts, ci, dm.seq == 2)];
@@ -332,6 +349,7 @@ __device__ __forceinline__ void t3_issuer(const T2Step* __restrict__ steps, cons
                     else { mbar_wait(&bars->opnd[1][net], opnd_c1 & 1u); opnd_c1++; }
                 }
                 tc_fence_after();
+                T3_TR(0x30 + t)          // operand of tile t ready
                 if (leader) {
                     if (fold) umma_bf16(acc, d_ones, d_bias, idesc, 0u);
                     if (src < 2) {
@@ -357,6 +375,7 @@ __device__ __forceinline__ void t3_issuer(const T2Step* __restrict__ steps, cons
                     if (t == ntile - 1) umma_commit(&bars->empty[it & smask]);   // all tiles' MMAs done -> slot free
                 }
                 __syncwarp();
+                T3_TR(0x40 + t)          // MMAs of tile t issued + committed
             }
         }
         // consume the final `fin` phase of both tiles (the q-density epilogues) to stay in step with the groups
@@ -382,6 +401,7 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
     uint8_t* bias_ring = m.bias_ring;
     const uint32_t h_stride = m.h_stride;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int trace_n = 0; (void)trace_n;
     X3 x;
     x.lane = lane; x.g = (warp >> 3) & 1; x.part = (warp >> 2) & 1; x.row = (warp & 3) * 32 + lane;
     x.tb = tmem_base + (uint32_t)x.g * kT3TileCols + ((uint32_t)((warp & 3) * 32) << 16);
@@ -464,7 +484,9 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
 #pragma unroll 1
                 for (int net = 0; net < 2; ++net) {
                     const uint32_t bias = x.bias_ring + (uint32_t)(net * 4 + ((x.chunk_it >> 1) & 3)) * kT3BiasEntry;
+                    T3_TR(0x10 + net)        // waiting for the MMAs of this net
                     wait_mma3(x, net);
+                    T3_TR(0x12 + net)        // accumulator ready: epilogue starts
                     const uint32_t acc = x.tb + (net ? kT3Acc1 : kT3Acc0);
                     const uint32_t ohi = x.h_base + (uint32_t)(net * 2) * h_stride, olo = ohi + h_stride;
                     epi_layer3<NPASS, ACT_R, false, true, !FOLD_D>(acc, ohi, olo, bias, 0u, x.part, Wd, koff_d);
@@ -476,8 +498,10 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
             const float* bias_mu = reinterpret_cast<const float*>(bias_ring + (size_t)(0 * 4 + ((x.chunk_it >> 1) & 3)) * kT3BiasEntry);
             const float* bias_ls = reinterpret_cast<const float*>(bias_ring + (size_t)(1 * 4 + ((x.chunk_it >> 1) & 3)) * kT3BiasEntry);
             x.chunk_it += 2;
+            T3_TR(0x14)              // waiting for both L3 outputs
             wait_mma3(x, 0);
             wait_mma3(x, 1);
+            T3_TR(0x15)              // E2 / E3 phase starts
             if (which == 0) {
                 // sample u = exp(ls) eps + mu (fastpredNF.py:727-733) -> [u, mx] operand; log r = -C/2 log 2pi - sum ls - 1/2 sum eps^2
                 if (INV) {      // modules reversed: the last block's BatchNorm.inverse comes first (TFCondARFlow.py:264-269)
@@ -560,6 +584,7 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
                 lacc += INV ? -lp_u : lp_u;                                                // forward: +log q, inverse: -log r
             }
             warp_arrive3(x, &bars->fin[g]);
+            T3_TR(0x16)              // E2 / E3 phase done
             if (which == 1) break;
 
             // ============ n_blocks x (masked affine coupling + BatchNorm), forward ============
@@ -575,7 +600,9 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
                     for (int net = 0; net < 2; ++net) {
                         const uint32_t tail = x.bias_ring + (uint32_t)(net * 4 + ((x.chunk_it >> 1) & 3)) * kT3BiasEntry;
                         x.chunk_it++;
+                        T3_TR(0x10 + net)
                         wait_mma3(x, net);
+                        T3_TR(0x12 + net)
                         const uint32_t acc = x.tb + (net ? kT3Acc1 : kT3Acc0);
                         const uint32_t ohi = x.h_base + (uint32_t)(net * 2) * h_stride, olo = ohi + h_stride;
                         if (!last) {

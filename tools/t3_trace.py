@@ -1,0 +1,67 @@
+"""Development aid: event timeline of CTA 0 of the two-tile kernel (library built with -DFC_T3_TRACE=1, pointed to by
+FLOWCHAIN_B200_LIB).  Prints, for steady-state items, how the epilogue warps of the two tiles and the two MMA issuers
+spend their time: busy in an epilogue, waiting for MMAs, waiting for operands."""
+import ctypes, os, sys, numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from flowchain_iccv2023_b200 import synth, _lib
+from flowchain_iccv2023_b200.flow import fastpredNF_CIF_separate_cond
+spec = synth.DEFAULT_SPEC
+f = fastpredNF_CIF_separate_cond(2, 3, 64, 2, 16, flow_architecture='realNVP', pred_len=12)
+f.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_params(spec, 0).items()})
+f = f.cuda().eval()
+A = 64
+inp = synth.make_inputs(spec, A, 1)
+grid = torch.from_numpy(synth.make_grid(256)).cuda()
+bp, cd = torch.from_numpy(inp['base_pos']).cuda(), torch.from_numpy(inp['cond']).cuda()
+lib = _lib.load()
+lib.fc_debug_t3trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
+prec = _lib.FC_PREC_F16X3
+f.grid_log_prob(bp, cd, grid, seed=1, precision=prec); torch.cuda.synchronize()
+lib.fc_debug_t3trace(None, 1)
+f.grid_log_prob(bp, cd, grid, seed=2, precision=prec); torch.cuda.synchronize()
+buf = (ctypes.c_ulonglong * (20 * 1024))()
+lib.fc_debug_t3trace(buf, 0)
+a = np.array(buf[:], dtype=np.uint64).reshape(20, 1024)
+# NOTE: two launches per pass write the same buffer; the second launch (steps 8-11) overwrites from index 0 of each warp
+def events(w):
+    out = []
+    for v in a[w]:
+        if v: out.append((int(v & np.uint64(0xFFFFFFFFFFFF)), int(v >> np.uint64(48))))
+    return out
+def summarize_compute(w):
+    ev = events(w)
+    busy = wait = phase = 0
+    n = 0
+    for (t0, g0), (t1, g1) in zip(ev, ev[1:]):
+        if t1 < t0: continue          # launch boundary
+        d = t1 - t0
+        if g0 in (0x10, 0x11, 0x14): wait += d          # waiting for MMAs
+        elif g0 in (0x12, 0x13): busy += d              # hidden-layer epilogue (until the next wait starts)
+        elif g0 == 0x15: phase += d                     # E2 / E3
+        elif g0 == 0x16: busy += d                      # coupling tail / gather until next wait
+        n += 1
+    tot = busy + wait + phase
+    return busy, phase, wait, tot, n
+print("epilogue warps (lane 0 of the first warp of each column part), share of traced time:")
+for w in (0, 4, 8, 12):
+    b, p, wt, tot, n = summarize_compute(w)
+    if tot: print(f"  warp {w:2d} (tile {w // 8}, part {(w // 4) % 2}): epilogue+tails {100 * b / tot:5.1f} %  E2/E3 {100 * p / tot:5.1f} %  waiting for MMAs {100 * wt / tot:5.1f} %  ({n} events, {tot} cycles)")
+for w in (17, 18):
+    ev = events(w)
+    wait_w = wait_o = issue = 0
+    for (t0, g0), (t1, g1) in zip(ev, ev[1:]):
+        if t1 < t0: continue
+        d = t1 - t0
+        if g1 == 0x20: wait_w += d                       # until the weight chunk landed
+        elif g1 in (0x30, 0x31): wait_o += d             # until the operand was ready
+        elif g1 in (0x40, 0x41): issue += d              # issuing MMAs
+    tot = wait_w + wait_o + issue
+    if tot: print(f"  issuer warp {w}: waiting for weights {100 * wait_w / tot:5.1f} %  waiting for operands {100 * wait_o / tot:5.1f} %  issuing {100 * issue / tot:5.1f} %")
+# a short raw timeline of one steady-state stretch
+allev = []
+for w in (16, 17):
+    allev += [(t, w, g) for t, g in events(w)[200:280]]
+allev.sort()
+if allev:
+    t0 = allev[0][0]
+    for t, w, g in allev[:150]: print(f"{t - t0:8d}  warp {w:2d}  tag {g:#x}")
