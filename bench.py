@@ -8,7 +8,7 @@ reference call flow.log_prob(base_pos, g.expand(T), cond)) -- per G
 rank evaluates its own 64 agents (weak scaling, no data-path collective) and ONE all-gather assembles the
 (N*64, T, G) density maps on every rank inside the timed step.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|bf16]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|f16x3|f16]
 
 `--impl reference` times the reference algorithm's CPU port (oracle/, numpy fp32, all host threads BLAS
 uses) on a bounded sample of the same workload; /root/reference does not exist on the GPU box.
@@ -248,7 +248,7 @@ def run_ours(args):
     flow.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
     flow = flow.to(dev).eval()
     flow.check_versions = False
-    prec = {"fp32": _lib.FC_PREC_FP32, "bf16": _lib.FC_PREC_BF16, "f16x3": _lib.FC_PREC_F16X3, "f16": _lib.FC_PREC_F16}[args.precision]
+    prec = {"fp32": _lib.FC_PREC_FP32, "f16x3": _lib.FC_PREC_F16X3, "f16": _lib.FC_PREC_F16}[args.precision]
     flow.precision = prec
     handle = flow.engine()
 
@@ -386,7 +386,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "bf16": "bf16 operands / f32 accumulate", "f16": "f16 operands / f32 accumulate",
+            "dtype": {"fp32": "f32", "f16": "f16 operands / f32 accumulate",
                       "f16x3": "split-f16 operands (3 tcgen05 passes) / f32 accumulate"}[args.precision], "data": "synthetic",
             "config": {"workload": f"{'config2' if (A, n) == (64, 256) else ('config4 shard' if n == 512 else 'custom')}: {A} agents x {T} steps x {n}x{n} lattice per GPU, separate density (flow.log_prob), prefix self",
                        "model": "default ETH CIF_separate_cond (T=12,C0=16,H=64,3 blocks), random-init weights",
@@ -423,7 +423,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("FLOWCHAIN_PRECISION", "f16x3"), choices=["fp32", "bf16", "f16x3", "f16"])
+    ap.add_argument("--precision", default=os.environ.get("FLOWCHAIN_PRECISION", "f16x3"), choices=["fp32", "f16x3", "f16"])
     ap.add_argument("--agents", type=int, default=64)
     ap.add_argument("--grid", type=int, default=256)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

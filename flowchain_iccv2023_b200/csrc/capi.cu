@@ -12,14 +12,11 @@
 
 #include "../../include/flowchain_b200.h"
 #include "kernels_fp32.cuh"
-#include "kernels_tc.cuh"
-#include "kernels_tc2.cuh"
 #include "kernels_tc3.cuh"
 #include "plan.h"
+#include "tc_f16x3.cuh"
+#include "tc_host.cuh"
 
-#ifndef FC_T2_PARTS
-#define FC_T2_PARTS 2
-#endif
 using namespace fc;
 
 struct fc_handle {
@@ -33,16 +30,11 @@ struct fc_handle {
     StepPlan* d_plans = nullptr;
     float* d_wbuf = nullptr;          // packed fp32 weights
     size_t wbuf_floats = 0;
-    unsigned char* d_tc = nullptr;    // packed bf16 tensor-core image
-    size_t tc_bytes = 0;
-    fc::TcStep* d_tcsteps = nullptr;
-    fc::TcDims tcdims{};
     // accurate tensor-core path: [0] = 3-pass split fp16 (f16x3), [1] = single-pass fp16
     unsigned char* d_t2img[2] = {nullptr, nullptr};
     fc::T2Step* d_t2steps[2] = {nullptr, nullptr};
     fc::T2Dims t2dims[2]{};
     std::vector<fc::T2Step> t2steps_host[2];
-    int tc_kernel = 3;                // 3: two resident tiles per CTA (kernels_tc3.cuh), 2: one tile (kernels_tc2.cuh)
     float* d_upd = nullptr;           // rapid update: per-(agent, chunk) partial sums
     size_t upd_floats = 0;
     float* d_scratch = nullptr;       // K>1 importance-sample staging
@@ -72,6 +64,18 @@ static int fail(fc_handle* h, const char* fmt, ...) {
     } while (0)
 
 static inline int pad8(int v) { return (v + 7) / 8 * 8; }
+
+// Entry points run on the handle's device and give the caller's current device back on return.
+struct DevGuard {
+    int prev = -1, dev;
+    explicit DevGuard(int d) : dev(d) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DevGuard() {
+        if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+    }
+};
 
 static int check_desc(const fc_model_desc* d, fc_handle* h) {
     if (!d) return fail(h, "null model desc");
@@ -113,7 +117,6 @@ extern "C" int fc_create(fc_handle** out, const fc_model_desc* desc, int device)
     h->desc = *desc;
     h->device = device;
     h->smem_optin = (int)prop.sharedMemPerBlockOptin;
-    if (const char* e = getenv("FLOWCHAIN_TC_KERNEL")) h->tc_kernel = atoi(e) == 2 ? 2 : 3;   // development switch
     h->num_sms = prop.multiProcessorCount;
     *out = h;
     return 0;
@@ -121,11 +124,9 @@ extern "C" int fc_create(fc_handle** out, const fc_model_desc* desc, int device)
 
 extern "C" void fc_destroy(fc_handle* h) {
     if (!h) return;
-    cudaSetDevice(h->device);
+    DevGuard guard(h->device);
     cudaFree(h->d_plans);
     cudaFree(h->d_wbuf);
-    cudaFree(h->d_tc);
-    cudaFree(h->d_tcsteps);
     for (int i = 0; i < 2; ++i) { cudaFree(h->d_t2img[i]); cudaFree(h->d_t2steps[i]); }
     cudaFree(h->d_scratch);
     cudaFree(h->d_upd);
@@ -178,7 +179,7 @@ extern "C" int fc_load_weights(fc_handle* h, const float* blob, size_t n_floats,
     if (n_floats != fc_weight_blob_floats(&d))
         return fail(h, "weight blob has %zu floats, expected %zu for this model", n_floats, fc_weight_blob_floats(&d));
     cudaStream_t stream = (cudaStream_t)stream_;
-    FC_CUDA(h, cudaSetDevice(h->device));
+    DevGuard guard(h->device);
     const int T = d.pred_len, D = 2, H = d.hidden_size, HH = pad8(H);
     Reader rd{blob, n_floats};
     const float* var = rd.take((size_t)T * D);
@@ -258,26 +259,12 @@ extern "C" int fc_load_weights(fc_handle* h, const float* blob, size_t n_floats,
     h->E = eoff; h->Eseq = seoff;
     h->dims.in_rows = cmax; h->dims.u_rows = cmax; h->dims.h_rows = hmax; h->dims.T = T; h->dims.C0 = d.cond_size;
 
-    // bf16 tensor-core image (only for shapes that path supports; otherwise tc_bytes stays 0)
-    std::vector<unsigned char> tc_img;
-    std::vector<fc::TcStep> tc_steps;
-    fc::tc_pack(d, plans, tcsrc, tc_img, tc_steps, h->tcdims);
-
     FC_CUDA(h, cudaFree(h->d_plans)); h->d_plans = nullptr;
     FC_CUDA(h, cudaFree(h->d_wbuf)); h->d_wbuf = nullptr;
-    FC_CUDA(h, cudaFree(h->d_tc)); h->d_tc = nullptr;
-    FC_CUDA(h, cudaFree(h->d_tcsteps)); h->d_tcsteps = nullptr;
     FC_CUDA(h, cudaMalloc(&h->d_plans, sizeof(StepPlan) * T));
     FC_CUDA(h, cudaMalloc(&h->d_wbuf, buf.size() * sizeof(float)));
     FC_CUDA(h, cudaMemcpyAsync(h->d_plans, plans.data(), sizeof(StepPlan) * T, cudaMemcpyHostToDevice, stream));
     FC_CUDA(h, cudaMemcpyAsync(h->d_wbuf, buf.data(), buf.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
-    h->tc_bytes = tc_img.size();
-    if (h->tc_bytes) {
-        FC_CUDA(h, cudaMalloc(&h->d_tc, h->tc_bytes));
-        FC_CUDA(h, cudaMemcpyAsync(h->d_tc, tc_img.data(), h->tc_bytes, cudaMemcpyHostToDevice, stream));
-        FC_CUDA(h, cudaMalloc(&h->d_tcsteps, sizeof(fc::TcStep) * T));
-        FC_CUDA(h, cudaMemcpyAsync(h->d_tcsteps, tc_steps.data(), sizeof(fc::TcStep) * T, cudaMemcpyHostToDevice, stream));
-    }
     for (int i = 0; i < 2; ++i) {
         std::vector<unsigned char> img2;
         std::vector<fc::T2Step> st2;
@@ -287,9 +274,10 @@ extern "C" int fc_load_weights(fc_handle* h, const float* blob, size_t n_floats,
         FC_CUDA(h, cudaFree(h->d_t2steps[i])); h->d_t2steps[i] = nullptr;
         if (h->t2dims[i].supported) {
             FC_CUDA(h, cudaMalloc(&h->d_t2img[i], img2.size()));
-            FC_CUDA(h, cudaMemcpy(h->d_t2img[i], img2.data(), img2.size(), cudaMemcpyHostToDevice));
+            // pageable sources: cudaMemcpyAsync returns once they are staged, so the vectors may go out of scope
+            FC_CUDA(h, cudaMemcpyAsync(h->d_t2img[i], img2.data(), img2.size(), cudaMemcpyHostToDevice, stream));
             FC_CUDA(h, cudaMalloc(&h->d_t2steps[i], sizeof(fc::T2Step) * T));
-            FC_CUDA(h, cudaMemcpy(h->d_t2steps[i], st2.data(), sizeof(fc::T2Step) * T, cudaMemcpyHostToDevice));
+            FC_CUDA(h, cudaMemcpyAsync(h->d_t2steps[i], st2.data(), sizeof(fc::T2Step) * T, cudaMemcpyHostToDevice, stream));
         }
     }
     FC_CUDA(h, cudaStreamSynchronize(stream));
@@ -309,10 +297,12 @@ constexpr int kR = 64;
 int ready(fc_handle* h) {
     if (!h) return fail(nullptr, "null handle");
     if (!h->loaded) return fail(h, "weights not loaded (call fc_load_weights first)");
-    cudaError_t e = cudaSetDevice(h->device);
-    if (e != cudaSuccess) return fail(h, "cudaSetDevice: %s", cudaGetErrorString(e));
     return 0;
 }
+// every compute entry point: validate the handle, then run on its device (restored on return)
+#define FC_ENTER(h)           \
+    if (ready(h)) return 1;   \
+    DevGuard guard_((h)->device)
 
 template <typename Kern>
 int prep_kernel(fc_handle* h, Kern kern, size_t smem) {
@@ -329,30 +319,24 @@ int launch_density(fc_handle* h, RowArgs a, Mode mode, int precision, cudaStream
     const int T = h->desc.pred_len;
     const long long tiles = (a.N + kR - 1) / kR;
     if (tiles > 0x7fffffffLL) return fail(h, "too many rows (%lld)", a.N);
-    if (precision == FC_PREC_BF16) {
-        if (mode != MODE_SEPARATE) return fail(h, "the bf16 tensor-core path implements the per-step density only");
-        std::string msg;
-        int rc = fc::tc_launch_separate(h->tcdims, h->d_tcsteps, h->d_tc, a, h->num_sms, h->smem_optin, stream, &h->launches, &msg);
-        if (rc) return fail(h, "%s", msg.c_str());
-        return 0;
-    }
+    if (precision == FC_PREC_BF16)
+        return fail(h, "FC_PREC_BF16 (single-pass bf16 operands) was retired: ~1e-1 nats, it fails the 5e-3 tensor-core bar; use "
+                       "FC_PREC_F16 (same speed, ~3e-2 nats) or FC_PREC_F16X3 (5e-3 nats)");
     if (precision == FC_PREC_F16X3 || precision == FC_PREC_F16) {
         std::string msg;
         const int i = precision == FC_PREC_F16X3 ? 0 : 1;
-        if (mode == MODE_SEQUENTIAL) {      // chain mode runs on the two-tile kernel only
-            int rcs = i == 0 ? fc::tc3_launch_sequential<3>(h->t2dims[0], h->t2steps_host[0], h->d_t2steps[0], h->d_t2img[0], a, h->num_sms, h->smem_optin, stream, &h->launches, &msg)
-                             : fc::tc3_launch_sequential<1>(h->t2dims[1], h->t2steps_host[1], h->d_t2steps[1], h->d_t2img[1], a, h->num_sms, h->smem_optin, stream, &h->launches, &msg);
-            if (rcs) return fail(h, "%s", msg.c_str());
-            return 0;
+        int rc;
+        if (h->t2dims[i].supported) {       // narrow models (every layer <= 80 wide): two resident tiles per CTA
+            if (mode == MODE_SEQUENTIAL)
+                rc = i == 0 ? fc::tc3_launch_sequential<3>(h->t2dims[0], h->t2steps_host[0], h->d_t2steps[0], h->d_t2img[0], a, h->num_sms, h->smem_optin, stream, &h->launches, &msg)
+                            : fc::tc3_launch_sequential<1>(h->t2dims[1], h->t2steps_host[1], h->d_t2steps[1], h->d_t2img[1], a, h->num_sms, h->smem_optin, stream, &h->launches, &msg);
+            else
+                rc = i == 0 ? fc::tc3_launch_separate<3>(h->t2dims[0], h->t2steps_host[0], h->d_t2steps[0], h->d_t2img[0], a, h->num_sms, h->smem_optin, stream, &h->launches, &msg)
+                            : fc::tc3_launch_separate<1>(h->t2dims[1], h->t2steps_host[1], h->d_t2steps[1], h->d_t2img[1], a, h->num_sms, h->smem_optin, stream, &h->launches, &msg);
+        } else {
+            msg = "the tensor-core path does not support this model shape; use FC_PREC_FP32";
+            rc = 1;
         }
-        if (h->tc_kernel == 3) {
-            int rc3 = i == 0 ? fc::tc3_launch_separate<3>(h->t2dims[0], h->t2steps_host[0], h->d_t2steps[0], h->d_t2img[0], a, h->num_sms, h->smem_optin, stream, &h->launches, &msg)
-                             : fc::tc3_launch_separate<1>(h->t2dims[1], h->t2steps_host[1], h->d_t2steps[1], h->d_t2img[1], a, h->num_sms, h->smem_optin, stream, &h->launches, &msg);
-            if (rc3) return fail(h, "%s", msg.c_str());
-            return 0;
-        }
-        int rc = i == 0 ? fc::tc2_launch_separate<3, FC_T2_PARTS>(h->t2dims[0], h->d_t2steps[0], h->d_t2img[0], a, h->num_sms, h->smem_optin, stream, &h->launches, &msg)
-                        : fc::tc2_launch_separate<1, FC_T2_PARTS>(h->t2dims[1], h->d_t2steps[1], h->d_t2img[1], a, h->num_sms, h->smem_optin, stream, &h->launches, &msg);
         if (rc) return fail(h, "%s", msg.c_str());
         return 0;
     }
@@ -399,7 +383,7 @@ int seq_bounds(fc_handle* h, int n_step, int* klo, int* jlo) {
 
 extern "C" int fc_log_prob(fc_handle* h, const float* base_pos, const float* x, const float* cond, const float* eps,
                            uint64_t seed, float* out, int64_t N, int precision, void* stream) {
-    if (ready(h)) return 1;
+    FC_ENTER(h);
     if (N < 0) return fail(h, "negative row count");
     if (N > 0 && (!base_pos || !x || !cond || !out)) return fail(h, "null tensor pointer");
     const int T = h->desc.pred_len, C0 = h->desc.cond_size;
@@ -417,7 +401,7 @@ extern "C" int fc_log_prob(fc_handle* h, const float* base_pos, const float* x, 
 extern "C" int fc_log_prob_sequential(fc_handle* h, const float* base_pos, const float* x, const float* cond,
                                       const float* eps, uint64_t seed, int n_step, float* out, int64_t N,
                                       int precision, void* stream) {
-    if (ready(h)) return 1;
+    FC_ENTER(h);
     if (N < 0) return fail(h, "negative row count");
     if (N > 0 && (!base_pos || !x || !cond || !out)) return fail(h, "null tensor pointer");
     const int T = h->desc.pred_len, C0 = h->desc.cond_size;
@@ -437,7 +421,7 @@ static int grid_log_prob_impl(fc_handle* h, const float* base_pos, const float* 
                               const float* grid, const float* eps, uint64_t seed, int prefix_mode, int sequential,
                               int K, float* out, int64_t out_agent_stride, int64_t out_point_stride,
                               int64_t out_step_stride, int64_t A, int64_t G, int precision, void* stream_, int multicast) {
-    if (ready(h)) return 1;
+    FC_ENTER(h);
     cudaStream_t stream = (cudaStream_t)stream_;
     if (A < 0 || G < 0) return fail(h, "negative size");
     if (K < 1 || K > 4096) return fail(h, "K must be in [1, 4096], got %d", K);
@@ -500,7 +484,7 @@ extern "C" int fc_grid_log_prob_multicast(fc_handle* h, const float* base_pos, c
 extern "C" int fc_sample_with_log_prob(fc_handle* h, const float* base_pos, const float* cond, const float* z0,
                                        const float* eps, uint64_t seed, float* seq, float* log_prob, float* ldjs,
                                        float* base_lp, int64_t B, int64_t S, int precision, void* stream) {
-    if (ready(h)) return 1;
+    FC_ENTER(h);
     if (B < 0 || S < 0) return fail(h, "negative size");
     if (B == 0 || S == 0) return 0;
     if (!base_pos || !cond || !seq || !log_prob || !ldjs || !base_lp) return fail(h, "null tensor pointer");
@@ -540,7 +524,7 @@ extern "C" int fc_sample_with_log_prob(fc_handle* h, const float* base_pos, cons
 }
 
 extern "C" int fc_base_normalizer(fc_handle* h, const float* base_lp, float* normalizer, int64_t A, int64_t S, void* stream) {
-    if (ready(h)) return 1;
+    FC_ENTER(h);
     if (A <= 0 || S <= 0) return A < 0 || S < 0 ? fail(h, "negative size") : 0;
     if (!base_lp || !normalizer) return fail(h, "null tensor pointer");
     k_base_normalizer<<<(unsigned)A, 512, 0, (cudaStream_t)stream>>>(base_lp, normalizer, S);
@@ -551,7 +535,7 @@ extern "C" int fc_base_normalizer(fc_handle* h, const float* base_lp, float* nor
 
 extern "C" int fc_update(fc_handle* h, const float* new_pos, int t, const float* prob_st_0, const float* ldjs,
                          const float* normalizer, float* prob_st_t, int64_t A, int64_t S, void* stream) {
-    if (ready(h)) return 1;
+    FC_ENTER(h);
     const int T = h->desc.pred_len;
     if (!(0 < t && t < T)) return fail(h, "time_step for update need to be 0~%d, got %d", T - 1, t);
     if (A < 0 || S < 0) return fail(h, "negative size");
@@ -584,17 +568,9 @@ extern "C" int fc_tc_gemm_selftest(const float* A, const float* B, float* D, int
     return rc;
 }
 
-// development aid: per-phase cycle counters of the tensor-core kernel (only filled when built with -DFC_T2_PROF=1)
-extern "C" int fc_debug_t2prof(unsigned long long* out16, int reset) {
-    if (out16 && cudaMemcpyFromSymbol(out16, fc::g_t2prof, sizeof(unsigned long long) * 16) != cudaSuccess) return 1;
-    if (reset) {
-        unsigned long long z[16] = {0};
-        if (cudaMemcpyToSymbol(fc::g_t2prof, z, sizeof z) != cudaSuccess) return 1;
-    }
-    return 0;
-}
-
-extern "C" int fc_debug_t3trace(unsigned long long* out, int reset) {   // 20 x 1024 entries, (tag << 48) | clock (needs -DFC_T3_TRACE=1)
+#if FC_T3_TRACE
+// development aid (-DFC_T3_TRACE=1 builds only, not part of the shipped ABI): event trace of CTA 0
+extern "C" int fc_debug_t3trace(unsigned long long* out, int reset) {   // 20 x 1024 entries, (tag << 48) | clock
     if (out && cudaMemcpyFromSymbol(out, fc::g_t3trace, sizeof(unsigned long long) * 20 * 1024) != cudaSuccess) return 1;
     if (reset) {
         static unsigned long long z[20 * 1024];
@@ -602,12 +578,4 @@ extern "C" int fc_debug_t3trace(unsigned long long* out, int reset) {   // 20 x 
     }
     return 0;
 }
-
-extern "C" int fc_debug_t2trace(unsigned long long* out, int reset) {   // 12 x 256 entries, (tag << 48) | clock
-    if (out && cudaMemcpyFromSymbol(out, fc::g_t2trace, sizeof(unsigned long long) * 12 * 256) != cudaSuccess) return 1;
-    if (reset) {
-        static unsigned long long z[12 * 256];
-        if (cudaMemcpyToSymbol(fc::g_t2trace, z, sizeof z) != cudaSuccess) return 1;
-    }
-    return 0;
-}
+#endif

@@ -1,6 +1,6 @@
 // kernels_tc3.cuh -- f16x3 / f16 tensor-core per-step density with TWO resident 128-row tiles per CTA.
 //
-// Same arithmetic as kernels_tc2.cuh (split-fp16 operands, tcgen05.mma, fp32 accumulate; see there), re-organised so
+// Split-fp16 operands, tcgen05.mma, fp32 accumulate (arithmetic helpers and the weight image: tc_f16x3.cuh), organised so
 // that two independent tiles share one SM: tensor memory can hold only one tile when every operand lives in it
 // (480 of 512 columns), so here the HIDDEN-layer operands go to shared memory (SS-mode MMA, canonical K-major tiles
 // written by the epilogue) and tensor memory keeps just the accumulators and the two narrow first-layer operands
@@ -10,7 +10,8 @@
 // epilogues overlap each other and the other tile's MMAs, which hides the MMA -> epilogue -> MMA latency chain that
 // bounds the single-tile kernel.
 #pragma once
-#include "kernels_tc2.cuh"
+#include "kernels_fp32.cuh"
+#include "tc_f16x3.cuh"
 
 namespace fc {
 
@@ -42,13 +43,19 @@ struct T3Dims {
 #ifndef FC_T3_TRACE
 #define FC_T3_TRACE 0
 #endif
+#if FC_T3_TRACE
 __device__ unsigned long long g_t3trace[20][1024];
+#endif
+#if FC_T3_TRACE
 #define T3_TR(tag)                                                                                                      \
     if (FC_T3_TRACE && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && trace_n < 1024) {                                 \
         long long now_;                                                                                                 \
         asm volatile("mov.u64 %0, %%clock64;" : "=l"(now_));                                                            \
         g_t3trace[threadIdx.x >> 5][trace_n++] = ((unsigned long long)(tag) << 48) | ((unsigned long long)now_ & 0xFFFFFFFFFFFFull); \
     }
+#else
+#define T3_TR(tag)
+#endif
 
 namespace t3 {
 using namespace tc;
@@ -743,9 +750,9 @@ k_separate_tc3(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
     if (warp == 16) tmem_dealloc(tmem_base, 512);
 }
 
-// Launches the steps in groups of equal operand-width class: hidden width <= 64 -> this two-tile kernel (128 KB of
-// operand tiles + a 4-slot weight ring); wider steps (hidden 80: 160 KB of operand tiles leave no room for the ring)
-// -> the single-tile kernel of kernels_tc2.cuh.
+// Launches the steps in groups of equal operand-width class (hidden width <= 64: 128 KB of operand tiles + a 4-slot weight
+// ring; 80: 160 KB of operand tiles + 2 slots).  Models with wider layers never get here: tc2_pack refuses them and
+// capi.cu routes them to the single-tile wide kernel (kernels_tcw.cuh).
 template <int NPASS>
 inline int tc3_launch_separate(const T2Dims& dm2, const std::vector<T2Step>& hsteps, const T2Step* d_steps, const unsigned char* d_img,
                                const RowArgs& a, int num_sms, int smem_optin, cudaStream_t stream, uint64_t* launches, std::string* msg) {
@@ -759,7 +766,7 @@ inline int tc3_launch_separate(const T2Dims& dm2, const std::vector<T2Step>& hst
     while (lo < T) {
         // group consecutive steps with the same operand-width class
         // (the class also fixes which hidden layers carry folded biases: tc2_pack folds widths <= kFoldMaxN = 64)
-        auto wclass = [&](int s) { const int w = hsteps[s].Wd > hsteps[s].Hc ? hsteps[s].Wd : hsteps[s].Hc; return (w <= 64 ? 64 : 80) + (hsteps[s].Wd <= kFoldMaxN ? 1 : 0); };
+        auto wclass = [&](int s) { const int w = hsteps[s].Wd > hsteps[s].Hc ? hsteps[s].Wd : hsteps[s].Hc; return (w <= 64 ? 64 : (w <= 80 ? 80 : 96)) + (hsteps[s].Wd <= kFoldMaxN ? 1 : 0); };
         int hi = lo;
         const int wc = wclass(lo) & ~1;
         const bool fold_d = hsteps[lo].Wd <= kFoldMaxN, fold_c = hsteps[lo].Hc <= kFoldMaxN;
@@ -775,12 +782,7 @@ inline int tc3_launch_separate(const T2Dims& dm2, const std::vector<T2Step>& hst
         // pipeline; 4 when they fit
         dm.nslots_log2 = (fixed + (size_t)4 * slot <= (size_t)smem_optin) ? 2 : 1;
         const size_t smem = fixed + ((size_t)1 << dm.nslots_log2) * slot;
-        if (smem > (size_t)smem_optin) {
-            int rc = tc2_launch_separate<NPASS, 2>(dm2, d_steps, d_img, a, num_sms, smem_optin, stream, launches, msg, lo, hi);
-            if (rc) return rc;
-            lo = hi + 1;
-            continue;
-        }
+        if (wc > 80 || smem > (size_t)smem_optin) { *msg = "the two-tile tensor-core kernel does not fit this model shape"; return 1; }
         const long long items = pairs * (hi - lo + 1);
         const int grid = (int)(items < num_sms ? items : num_sms);
         cudaError_t e = cudaSuccess;

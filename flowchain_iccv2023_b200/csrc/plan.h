@@ -69,13 +69,14 @@ struct RowArgs {
     int fuse_k;            // 1: K = 2^j <= 32 importance samples of a point sit in consecutive rows (= lanes): logsumexp_k - log K
                            // is reduced with warp shuffles in registers and ONE value per (point, step) is stored
     int out_sys;           // 1: `out` is an NVSwitch multicast address of a symmetric buffer: every store is replicated to
-                           // all peers, so the density maps are all-gathered by the stores themselves (system-scope stores)
+                           // all peers, so the density maps are all-gathered by the stores themselves (multimem.st, system scope)
 };
 
 #ifdef __CUDACC__
 // the one place a log-density leaves the chip
 __device__ __forceinline__ void store_out(const RowArgs& a, long long idx, float v) {
-    if (a.out_sys) asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(a.out + idx), "f"(v) : "memory");
+    // multicast (multimem) addresses may only be accessed with multimem.* instructions (PTX ISA, "multimem.st")
+    if (a.out_sys) asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(a.out + idx), "f"(v) : "memory");
     else a.out[idx] = v;
 }
 // Result of row (agent ag, point-row rem = n % PPA) at output step `tidx`.  Must be reached by all 32 lanes of the warp

@@ -227,8 +227,6 @@ class fastpredNF_CIF_separate_cond(nn.Module):
         z0 = None if z0 is None else self._dev(z0).reshape(B * S, 2)
         eps = None if eps is None else self._dev(eps).reshape(B * S, -1)
         prec = self.precision if precision is None else precision
-        if prec == _lib.FC_PREC_BF16:        # the bf16 single-pass kernel implements the per-step density only
-            prec = _lib.FC_PREC_FP32
         outs = torch.ops.flowchain.sample_with_log_prob(h.id, bp, cd, S, z0, eps, self._seed(seed), prec)
         return tuple(o.to(src) for o in outs)
 

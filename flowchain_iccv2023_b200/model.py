@@ -149,6 +149,13 @@ class fastpredNF_TP(nn.Module):
     def load(self, path: Path = None) -> int:
         path = self.output_path / "ckpt.pt" if path is None else path
         ckpt = torch.load(path, map_location="cpu")
-        self.load_state_dict(ckpt["state"], strict=False)
+        # the reference loads strictly (fastpredNF.py:237-238).  Here the encoder is a pluggable callable that may or may
+        # not be an nn.Module registered on this wrapper, so only `encoder.*` keys may be absent / extra; every `flow.*`
+        # key must match, otherwise the kernels would silently run on random-init weights.
+        missing, unexpected = self.load_state_dict(ckpt["state"], strict=False)
+        bad = [k for k in list(missing) + list(unexpected) if not k.startswith("encoder.")]
+        if bad:
+            raise RuntimeError(f"checkpoint {path} does not match this model: missing/unexpected keys {bad[:8]}"
+                               f"{' ...' if len(bad) > 8 else ''} ({len(bad)} in total)")
         self.flow.invalidate()
         return ckpt["epoch"]

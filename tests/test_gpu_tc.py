@@ -1,4 +1,4 @@
-"""GPU tests of the tcgen05 tensor-core path (bf16 operands, fp32 accumulate)."""
+"""GPU tests of the tcgen05 tensor-core paths (split-fp16 "f16x3" and single-pass fp16 operands, fp32 accumulate)."""
 import ctypes
 
 import numpy as np
@@ -45,13 +45,12 @@ from flowchain_iccv2023_b200 import synth  # noqa: E402
 
 # Tolerances against the fp64 oracle, |d| <= atol + rtol*|ref64| nats:
 #   f16x3 (split-fp16, 3 MMA passes)  : the north_star tensor-core bar, 5e-3 nats (+ the fp32 relative floor 3e-6)
-#   f16 / bf16 (single pass)          : fast approximate modes.  Operand rounding (2^-11 / 2^-8) is amplified by
-#                                       |w - prev| / sigma^2 in the base term (sigma ~ 0.1), so their error is a
-#                                       few 1e-2 / 1e-1 nats on the [-3,3]^2 lattice; the bound below documents it.
+#   f16 (single pass)                 : fast approximate mode.  Operand rounding (2^-11) is amplified by
+#                                       |w - prev| / sigma^2 in the base term (sigma ~ 0.1), so its error is a
+#                                       few 1e-2 nats on the [-3,3]^2 lattice; the bound below documents it.
 MODES = {
     "f16x3": (_lib.FC_PREC_F16X3, 5e-3, 3e-6),
     "f16": (_lib.FC_PREC_F16, 0.05, 1e-3),
-    "bf16": (_lib.FC_PREC_BF16, 0.5, 1e-2),
 }
 
 
@@ -90,8 +89,6 @@ def test_tc_log_prob_golden(flow_default, mode):
 def test_tc_log_prob_sequential_golden(flow_default, mode):
     """Chain mode (flow.log_prob_sequential) on the two-tile tensor-core kernel: full chain and n_step variants.  The
     chain sums up to 12 step log-dets before dividing, so its tolerance is stated on the chain's own |ref|."""
-    if MODES[mode][0] == _lib.FC_PREC_BF16:
-        pytest.skip("the bf16 single-pass kernel implements the per-step density only")
     f, spec, p, g = flow_default
     out = f.log_prob_sequential(T(g["base_pos"]), T(g["x"]), T(g["cond"]), eps=T(g["eps_seq"]), precision=MODES[mode][0]).cpu().numpy()
     check("log_prob_sequential", out, g["log_prob_seq_64"], mode)
@@ -247,6 +244,13 @@ def test_config2_full_size_properties(flow_default):
     assert frac >= 0.9999 and worst < 3.0                            # fp32 itself is up to 3e-6 |ref| off
     rows = f.grid_log_prob(bp[:2], cd[:2], grid, seed=42, precision=_lib.FC_PREC_F16X3)          # (2, G, T) row order
     assert torch.equal(rows.transpose(1, 2), m1[:2])                 # same rows, same streams, other layout
+
+
+def test_bf16_mode_retired(flow_default):
+    """FC_PREC_BF16 (single-pass bf16, ~1e-1 nats) failed the 5e-3 bar and was removed: the call must say what to use."""
+    f, spec, p, g = flow_default
+    with pytest.raises(RuntimeError, match="FC_PREC_F16"):
+        f.log_prob(T(g["base_pos"]), T(g["x"]), T(g["cond"]), eps=T(g["eps"]), precision=_lib.FC_PREC_BF16)
 
 
 def test_tc_deep_blocks_golden():

@@ -89,3 +89,25 @@ def test_synth_is_deterministic():
         np.testing.assert_array_equal(a[k], b[k])
     assert synth.DEFAULT_SPEC.flops_separate_row() == 2136704
     assert synth.DEFAULT_SPEC.flops_sequential_row() == 12616448
+
+
+def test_wrapper_load_rejects_mismatched_flow_keys(tmp_path):
+    """model.load tolerates only `encoder.*` differences (the reference loads strictly, fastpredNF.py:237-238): a
+    checkpoint whose flow.* section is truncated or renamed must raise instead of leaving random-init weights."""
+    from flowchain_iccv2023_b200.model import fastpredNF_TP
+    m = fastpredNF_TP(encoder=lambda d: None, pred_len=3, n_blocks=1, n_hidden=1, hidden_size=16, cond_size=4)
+    path = tmp_path / "ckpt.pt"
+    m.save(epoch=7, path=path)
+    assert m.load(path) == 7
+    state = dict(m.state_dict())
+    state["encoder.some.weight"] = torch.zeros(3)                   # a reference encoder's keys are ignored
+    torch.save({"epoch": 8, "state": state, "optim_state": {}}, path)
+    assert m.load(path) == 8
+    state.pop("flow.var")
+    torch.save({"epoch": 9, "state": state, "optim_state": {}}, path)
+    with pytest.raises(RuntimeError, match="flow.var"):
+        m.load(path)
+    state = {k.replace("flow.", "model."): v for k, v in m.state_dict().items()}
+    torch.save({"epoch": 9, "state": state, "optim_state": {}}, path)
+    with pytest.raises(RuntimeError, match="does not match"):
+        m.load(path)
