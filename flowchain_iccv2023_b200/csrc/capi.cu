@@ -13,6 +13,7 @@
 #include "../../include/flowchain_b200.h"
 #include "kernels_fp32.cuh"
 #include "kernels_tc3.cuh"
+#include "kernels_tcw.cuh"
 #include "plan.h"
 #include "tc_f16x3.cuh"
 #include "tc_host.cuh"
@@ -35,6 +36,11 @@ struct fc_handle {
     fc::T2Step* d_t2steps[2] = {nullptr, nullptr};
     fc::T2Dims t2dims[2]{};
     std::vector<fc::T2Step> t2steps_host[2];
+    // wide tensor-core path (kernels_tcw.cuh), same index convention; used when the two-tile kernel refuses the shape
+    unsigned char* d_twimg[2] = {nullptr, nullptr};
+    float* d_twtails[2] = {nullptr, nullptr};
+    fc::TwStep* d_twsteps[2] = {nullptr, nullptr};
+    fc::TwDims twdims[2]{};
     float* d_upd = nullptr;           // rapid update: per-(agent, chunk) partial sums
     size_t upd_floats = 0;
     float* d_scratch = nullptr;       // K>1 importance-sample staging
@@ -127,7 +133,10 @@ extern "C" void fc_destroy(fc_handle* h) {
     DevGuard guard(h->device);
     cudaFree(h->d_plans);
     cudaFree(h->d_wbuf);
-    for (int i = 0; i < 2; ++i) { cudaFree(h->d_t2img[i]); cudaFree(h->d_t2steps[i]); }
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(h->d_t2img[i]); cudaFree(h->d_t2steps[i]);
+        cudaFree(h->d_twimg[i]); cudaFree(h->d_twtails[i]); cudaFree(h->d_twsteps[i]);
+    }
     cudaFree(h->d_scratch);
     cudaFree(h->d_upd);
     delete h;
@@ -280,6 +289,24 @@ extern "C" int fc_load_weights(fc_handle* h, const float* blob, size_t n_floats,
             FC_CUDA(h, cudaMemcpyAsync(h->d_t2steps[i], st2.data(), sizeof(fc::T2Step) * T, cudaMemcpyHostToDevice, stream));
         }
     }
+    for (int i = 0; i < 2; ++i) {       // wide image only for the shapes the two-tile kernel does not take
+        FC_CUDA(h, cudaFree(h->d_twimg[i])); h->d_twimg[i] = nullptr;
+        FC_CUDA(h, cudaFree(h->d_twtails[i])); h->d_twtails[i] = nullptr;
+        FC_CUDA(h, cudaFree(h->d_twsteps[i])); h->d_twsteps[i] = nullptr;
+        memset(&h->twdims[i], 0, sizeof h->twdims[i]);
+        if (h->t2dims[i].supported) continue;
+        std::vector<unsigned char> imgw;
+        std::vector<float> tailsw;
+        std::vector<fc::TwStep> stw;
+        fc::tcw_pack(d, plans, tcsrc, i == 0 ? 3 : 1, imgw, tailsw, stw, h->twdims[i], h->smem_optin);
+        if (!h->twdims[i].supported) continue;
+        FC_CUDA(h, cudaMalloc(&h->d_twimg[i], imgw.size()));
+        FC_CUDA(h, cudaMemcpyAsync(h->d_twimg[i], imgw.data(), imgw.size(), cudaMemcpyHostToDevice, stream));
+        FC_CUDA(h, cudaMalloc(&h->d_twtails[i], tailsw.size() * sizeof(float)));
+        FC_CUDA(h, cudaMemcpyAsync(h->d_twtails[i], tailsw.data(), tailsw.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+        FC_CUDA(h, cudaMalloc(&h->d_twsteps[i], sizeof(fc::TwStep) * T));
+        FC_CUDA(h, cudaMemcpyAsync(h->d_twsteps[i], stw.data(), sizeof(fc::TwStep) * T, cudaMemcpyHostToDevice, stream));
+    }
     FC_CUDA(h, cudaStreamSynchronize(stream));
     h->plans = plans;
     h->wbuf_floats = buf.size();
@@ -333,9 +360,10 @@ int launch_density(fc_handle* h, RowArgs a, Mode mode, int precision, cudaStream
             else
                 rc = i == 0 ? fc::tc3_launch_separate<3>(h->t2dims[0], h->t2steps_host[0], h->d_t2steps[0], h->d_t2img[0], a, h->num_sms, h->smem_optin, stream, &h->launches, &msg)
                             : fc::tc3_launch_separate<1>(h->t2dims[1], h->t2steps_host[1], h->d_t2steps[1], h->d_t2img[1], a, h->num_sms, h->smem_optin, stream, &h->launches, &msg);
-        } else {
-            msg = "the tensor-core path does not support this model shape; use FC_PREC_FP32";
-            rc = 1;
+        } else {                            // wide models (hidden up to 256, cond up to 64): one tile per CTA, K-slab weight streaming
+            const int m = mode == MODE_SEQUENTIAL ? 1 : 0;
+            rc = i == 0 ? fc::tcw_launch<3>(h->twdims[0], h->d_twsteps[0], h->d_twimg[0], h->d_twtails[0], a, SampleOut{}, m, h->num_sms, h->smem_optin, stream, &h->launches, &msg)
+                        : fc::tcw_launch<1>(h->twdims[1], h->d_twsteps[1], h->d_twimg[1], h->d_twtails[1], a, SampleOut{}, m, h->num_sms, h->smem_optin, stream, &h->launches, &msg);
         }
         if (rc) return fail(h, "%s", msg.c_str());
         return 0;
@@ -501,8 +529,13 @@ extern "C" int fc_sample_with_log_prob(fc_handle* h, const float* base_pos, cons
     if (precision != FC_PREC_FP32) {     // tensor-core sampler: the two-tile kernel run in the inverse direction
         std::string msg;
         const int i = precision == FC_PREC_F16X3 ? 0 : 1;
-        int rc = i == 0 ? fc::tc3_launch_sample<3>(h->t2dims[0], h->t2steps_host[0], h->d_t2steps[0], h->d_t2img[0], a, o, h->num_sms, h->smem_optin, (cudaStream_t)stream, &h->launches, &msg)
+        int rc;
+        if (h->t2dims[i].supported)
+            rc = i == 0 ? fc::tc3_launch_sample<3>(h->t2dims[0], h->t2steps_host[0], h->d_t2steps[0], h->d_t2img[0], a, o, h->num_sms, h->smem_optin, (cudaStream_t)stream, &h->launches, &msg)
                         : fc::tc3_launch_sample<1>(h->t2dims[1], h->t2steps_host[1], h->d_t2steps[1], h->d_t2img[1], a, o, h->num_sms, h->smem_optin, (cudaStream_t)stream, &h->launches, &msg);
+        else
+            rc = i == 0 ? fc::tcw_launch<3>(h->twdims[0], h->d_twsteps[0], h->d_twimg[0], h->d_twtails[0], a, o, 2, h->num_sms, h->smem_optin, (cudaStream_t)stream, &h->launches, &msg)
+                        : fc::tcw_launch<1>(h->twdims[1], h->d_twsteps[1], h->d_twimg[1], h->d_twtails[1], a, o, 2, h->num_sms, h->smem_optin, (cudaStream_t)stream, &h->launches, &msg);
         if (rc) return fail(h, "%s", msg.c_str());
         return 0;
     }

@@ -9,7 +9,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-GOLDEN_CASES = ["default_eth", "odd_small", "deep_blocks", "stress_wide"]
+GOLDEN_CASES = ["default_eth", "odd_small", "deep_blocks", "stress_wide", "tuned_h128_c64", "config5_full"]
 
 
 def pytest_configure(config):

@@ -224,6 +224,10 @@ CASES = {
     "deep_blocks": dict(spec=synth.FlowSpec(pred_len=4, cond_size=16, hidden_size=64, n_hidden=2, n_blocks=6), seed=20, agents=4, grid_n=4, S=32),
     # config 5 stress knobs: 2x coupling layers, 256-wide conditioner MLPs (short chain so the fixture stays small)
     "stress_wide": dict(spec=synth.FlowSpec(pred_len=3, cond_size=16, hidden_size=256, n_hidden=2, n_blocks=6), seed=30, agents=3, grid_n=4, S=32),
+    # corner of the reference's own tuning range (src/main.py:222-229): HIDDEN_SIZE 128, CONDITIONING_LENGTH 64, N_HIDDEN 3
+    "tuned_h128_c64": dict(spec=synth.FlowSpec(pred_len=12, cond_size=64, hidden_size=128, n_hidden=3, n_blocks=3), seed=40, agents=4, grid_n=4, S=24),
+    # BASELINE config 5 at full model size: 12 steps x 6 coupling blocks x 256-wide conditioner MLPs (20 M parameters)
+    "config5_full": dict(spec=synth.FlowSpec(pred_len=12, cond_size=16, hidden_size=256, n_hidden=2, n_blocks=6), seed=50, agents=3, grid_n=3, S=16),
 }
 
 

@@ -299,3 +299,121 @@ def test_grid_log_prob_to_host_overlapped(flow_default):
         ref = f.grid_log_prob(T(inp["base_pos"][lo:hi]), T(inp["cond"][lo:hi]), T(grid), seed=100 + i, map_layout=True,
                               precision=_lib.FC_PREC_F16X3).cpu()
         assert torch.equal(out[lo:hi], ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# wide tensor-core kernel (kernels_tcw.cuh): hidden sizes up to 256, conditioning lengths up to 64
+# ------------------------------------------------------------------------------------------------
+WIDE_CASES = ["stress_wide", "tuned_h128_c64", "config5_full"]
+
+
+@pytest.fixture(scope="module")
+def wide_flows():
+    from flowchain_iccv2023_b200.flow import fastpredNF_CIF_separate_cond
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            spec, params, g = load_golden(name)
+            f = fastpredNF_CIF_separate_cond(2, spec.n_blocks, spec.hidden_size, spec.n_hidden, spec.cond_size,
+                                             flow_architecture="realNVP", pred_len=spec.pred_len)
+            f.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+            cache[name] = (f.cuda().eval(), spec, params, g)
+        return cache[name]
+    return get
+
+
+@pytest.mark.parametrize("case", WIDE_CASES)
+def test_wide_tc_density_golden(wide_flows, case):
+    """Per-step density, chain (full and n_step) and both grid prefix modes of the wide models on the tensor cores
+    (FC_PREC_F16X3) against the fp64 outputs of the unmodified reference, at the 5e-3 nats tensor-core bar."""
+    f, spec, p, g = wide_flows(case)
+    P = _lib.FC_PREC_F16X3
+    out = f.log_prob(T(g["base_pos"]), T(g["x"]), T(g["cond"]), eps=T(g["eps"]), precision=P).cpu().numpy()
+    check(case + " log_prob", out, g["log_prob_64"], "f16x3")
+    out = f.log_prob_sequential(T(g["base_pos"]), T(g["x"]), T(g["cond"]), eps=T(g["eps_seq"]), precision=P).cpu().numpy()
+    check(case + " log_prob_sequential", out, g["log_prob_seq_64"], "f16x3")
+    ns = min(3, spec.pred_len - 1)
+    out = f.log_prob_sequential(T(g["base_pos"]), T(g["x"]), T(g["cond"]), n_step=ns, eps=T(g["eps_seq"]), precision=P).cpu().numpy()
+    check(case + " log_prob_sequential n_step", out, g["log_prob_seq_n3_64"], "f16x3")
+    out = f.grid_log_prob(T(g["base_pos"]), T(g["cond"]), T(g["grid"]), eps=T(g["eps_grid"]), precision=P).cpu().numpy()
+    check(case + " grid self", out, g["grid_self_64"], "f16x3")
+    out = f.grid_log_prob(T(g["base_pos"]), T(g["cond"]), T(g["grid"]), cond_traj=T(g["cond_traj"]), eps=T(g["eps_grid"]),
+                          precision=P, map_layout=True).cpu().numpy()
+    check(case + " grid shared", out.transpose(0, 2, 1), g["grid_shared_64"], "f16x3")
+    out = f.log_prob(T(g["base_pos"]), T(g["x"]), T(g["cond"]), eps=T(g["eps"]), precision=_lib.FC_PREC_F16).cpu().numpy()
+    check(case + " log_prob (single-pass f16)", out, g["log_prob_64"], "f16")
+
+
+@pytest.mark.parametrize("case", WIDE_CASES)
+def test_wide_tc_sampler_golden(wide_flows, case):
+    """flow.sample_with_log_prob of the wide models on the tensor cores (inverse direction), golden tape (z0, eps)."""
+    f, spec, p, g = wide_flows(case)
+    B, S, D = g["z0"].shape
+    bp = T(g["base_pos"][:B])[:, None].expand(-1, S, -1)
+    cd = T(g["cond"][:B])[:, None].expand(-1, S, -1, -1)
+    seq, lp, ldjs, base = f.sample_with_log_prob(bp, cd, z0=T(g["z0"]), eps=T(g["eps_sample"]), precision=_lib.FC_PREC_F16X3)
+    err = np.abs(seq.cpu().numpy() - g["sample_seq_64"])
+    ref_abs = np.abs(g["sample_seq_64"])
+    print(f"[{case}] wide sampler positions: max|err| {err.max():.3e}  max|ref| {ref_abs.max():.1f}")
+    assert np.all(err <= 2e-4 + 1e-4 * ref_abs)
+    for name, out, ref in (("ldjs", ldjs, g["sample_ldjs_64"]), ("log_prob", lp, g["sample_log_prob_64"])):
+        out = out.cpu().numpy()
+        check(f"{case} wide sampler {name}", out, ref, "f16x3", frac=0.98)
+        np.testing.assert_allclose(out, ref, atol=5e-3, rtol=1e-4)
+    np.testing.assert_allclose(base.cpu().numpy(), g["sample_base_64"], atol=1e-4, rtol=3e-6)
+
+
+def test_config5_importance_K32_vs_oracle(wide_flows):
+    """BASELINE config 5 in one piece: 6 coupling blocks x 256-wide conditioner MLPs x K = 32 importance samples of the
+    CIF auxiliary variable (logsumexp_k - log K fused into the kernel with warp shuffles), tensor-core path and fp32
+    path against a Python loop of K fp64 oracle passes."""
+    f, spec, p, g = wide_flows("config5_full")
+    A, G, K = 2, 5, 32
+    inp = synth.make_inputs(spec, A, seed=60)
+    grid = synth.make_grid(3)[:G]
+    eps = synth.make_eps(spec, A * G * K, 61)
+    bp, x, cd = orc.grid_rows(inp["base_pos"], inp["cond"], grid)
+    e = eps.reshape(A * G, K, -1).transpose(1, 0, 2)
+    ref = orc.log_prob_importance(p, bp, x, cd, e, np.float64).reshape(A, G, -1)
+    out = f.grid_log_prob(T(inp["base_pos"]), T(inp["cond"]), T(grid), K=K, eps=T(eps), precision=_lib.FC_PREC_F16X3).cpu().numpy()
+    check("config5 K=32 f16x3", out, ref, "f16x3")
+    out32 = f.grid_log_prob(T(inp["base_pos"]), T(inp["cond"]), T(grid), K=K, eps=T(eps), precision=_lib.FC_PREC_FP32).cpu().numpy()
+    err = np.abs(out32 - ref)
+    assert np.all(err <= 1e-4 + 3e-6 * np.abs(ref)), err.max()
+
+
+@pytest.mark.parametrize("case", ["tuned_h128_c64", "config5_full"])
+def test_wide_tc_matches_fp32_path_at_scale(wide_flows, case):
+    """Same in-kernel Philox streams in both paths over a lattice (ragged tile count): wide tensor-core kernel vs the
+    fp32 CUDA-core kernel, per-step density and chain."""
+    f, spec, p, g = wide_flows(case)
+    inp = synth.make_inputs(spec, 3, seed=71)
+    grid = synth.make_grid(21)
+    for seqm in (False, True):
+        a32 = f.grid_log_prob(T(inp["base_pos"]), T(inp["cond"]), T(grid), sequential=seqm, seed=3, precision=_lib.FC_PREC_FP32).cpu().numpy()
+        a16 = f.grid_log_prob(T(inp["base_pos"]), T(inp["cond"]), T(grid), sequential=seqm, seed=3, precision=_lib.FC_PREC_F16X3).cpu().numpy()
+        check(f"{case} wide f16x3 vs fp32 kernels (philox, sequential={seqm})", a16, a32.astype(np.float64), "f16x3", frac=0.999)
+        assert np.max(np.abs(a16 - a32) / (5e-3 + 3e-6 * np.abs(a32))) < 3.0
+
+
+@pytest.mark.parametrize("kw", [dict(hidden_size=96, n_hidden=0), dict(pred_len=14), dict(hidden_size=80, cond_size=8),
+                                dict(hidden_size=112, cond_size=32, n_hidden=1, n_blocks=2)])
+def test_tc_width_routing_vs_oracle(kw):
+    """Shapes around the boundary between the two tensor-core kernels (layers <= 80 wide: two-tile kernel; wider: wide
+    kernel) must all land on a kernel that fits them: hidden 96 with no hidden layer, pred_len 14 (density nets 96 wide),
+    hidden 80 (the two-tile kernel's widest class), hidden 112 / cond 32 (inside the reference's tuning range)."""
+    from flowchain_iccv2023_b200.flow import fastpredNF_CIF_separate_cond
+    spec = synth.FlowSpec(**kw)
+    p = synth.make_params(spec, 77)
+    f = fastpredNF_CIF_separate_cond(2, spec.n_blocks, spec.hidden_size, spec.n_hidden, spec.cond_size,
+                                     flow_architecture="realNVP", pred_len=spec.pred_len)
+    f.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()}, strict=True)
+    f = f.cuda().eval()
+    N = 131
+    inp = synth.make_inputs(spec, N, seed=78)
+    x = (inp["base_pos"][:, None, :] + 0.5 * synth.normal(79, "x", (N, spec.pred_len, 2))).astype(np.float32)
+    eps = synth.make_eps(spec, N, 80)
+    ref = orc.log_prob(p, inp["base_pos"], x, inp["cond"], eps, np.float64)
+    out = f.log_prob(T(inp["base_pos"]), T(x), T(inp["cond"]), eps=T(eps), precision=_lib.FC_PREC_F16X3).cpu().numpy()
+    check(f"routing {kw}", out, ref, "f16x3")
