@@ -22,7 +22,7 @@ FC_PREFIX_SHARED = 1
 SYMBOLS = [
     "fc_create", "fc_destroy", "fc_last_error", "fc_weight_blob_floats", "fc_load_weights",
     "fc_weights_version", "fc_log_prob", "fc_log_prob_sequential", "fc_grid_log_prob", "fc_grid_log_prob_multicast",
-    "fc_sample_with_log_prob", "fc_base_normalizer", "fc_update", "fc_launch_count", "fc_tc_gemm_selftest",
+    "fc_sample_with_log_prob", "fc_base_normalizer", "fc_update", "fc_update_lazy", "fc_launch_count", "fc_tc_gemm_selftest",
 ]
 
 
@@ -74,6 +74,8 @@ def load():
     lib.fc_base_normalizer.restype = c_int
     lib.fc_update.argtypes = [c_void_p, fp, c_int, fp, fp, fp, fp, c_int64, c_int64, c_void_p]
     lib.fc_update.restype = c_int
+    lib.fc_update_lazy.argtypes = [c_void_p, fp, c_int, fp, fp, fp, c_int64, c_int64, c_void_p]
+    lib.fc_update_lazy.restype = c_int
     lib.fc_tc_gemm_selftest.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int]
     lib.fc_tc_gemm_selftest.restype = c_int
     lib.fc_launch_count.argtypes = [c_void_p]

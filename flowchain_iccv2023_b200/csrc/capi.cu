@@ -41,8 +41,6 @@ struct fc_handle {
     float* d_twtails[2] = {nullptr, nullptr};
     fc::TwStep* d_twsteps[2] = {nullptr, nullptr};
     fc::TwDims twdims[2]{};
-    float* d_upd = nullptr;           // rapid update: per-(agent, chunk) partial sums
-    size_t upd_floats = 0;
     float* d_scratch = nullptr;       // K>1 importance-sample staging
     size_t scratch_floats = 0;
     Dims dims{};
@@ -138,7 +136,6 @@ extern "C" void fc_destroy(fc_handle* h) {
         cudaFree(h->d_twimg[i]); cudaFree(h->d_twtails[i]); cudaFree(h->d_twsteps[i]);
     }
     cudaFree(h->d_scratch);
-    cudaFree(h->d_upd);
     delete h;
 }
 
@@ -476,7 +473,11 @@ static int grid_log_prob_impl(fc_handle* h, const float* base_pos, const float* 
         return launch_density(h, a, sequential ? MODE_SEQUENTIAL : MODE_SEPARATE, precision, stream);
     }
     const size_t need = (size_t)a.N * T;
-    if (need > h->scratch_floats) {
+    if (need > h->scratch_floats) {          // grows outside graph capture only (the one call that allocates: documented in the header)
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        FC_CUDA(h, cudaStreamIsCapturing(stream, &cs));
+        if (cs != cudaStreamCaptureStatusNone)
+            return fail(h, "K = %d needs a %zu-float staging buffer that is not allocated yet: run the call once outside graph capture", K, need);
         FC_CUDA(h, cudaStreamSynchronize(stream));
         FC_CUDA(h, cudaFree(h->d_scratch));
         h->d_scratch = nullptr; h->scratch_floats = 0;
@@ -566,32 +567,47 @@ extern "C" int fc_base_normalizer(fc_handle* h, const float* base_lp, float* nor
     return 0;
 }
 
-extern "C" int fc_update(fc_handle* h, const float* new_pos, int t, const float* prob_st_0, const float* ldjs,
-                         const float* normalizer, float* prob_st_t, int64_t A, int64_t S, void* stream) {
+static int update_impl(fc_handle* h, const float* new_pos, int t, const float* prob_st_0, const float* ldjs,
+                       const float* normalizer, float* out, int64_t A, int64_t S, void* stream, bool lazy) {
     FC_ENTER(h);
     const int T = h->desc.pred_len;
     if (!(0 < t && t < T)) return fail(h, "time_step for update need to be 0~%d, got %d", T - 1, t);
     if (A < 0 || S < 0) return fail(h, "negative size");
     if (A == 0 || S == 0) return 0;
-    if (!new_pos || !prob_st_0 || !ldjs || !normalizer || !prob_st_t) return fail(h, "null tensor pointer");
-    const int nchunk = (int)((S + kUpdChunk - 1) / kUpdChunk);
-    const size_t need = (size_t)A * nchunk;
-    if (need > h->upd_floats) {            // partial sums live in a handle-owned buffer (grown outside graph capture)
-        FC_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
-        FC_CUDA(h, cudaFree(h->d_upd));
-        h->d_upd = nullptr; h->upd_floats = 0;
-        FC_CUDA(h, cudaMalloc(&h->d_upd, need * sizeof(float)));
-        h->upd_floats = need;
-    }
+    if (!new_pos || !prob_st_0 || !normalizer || !out || (!lazy && !ldjs)) return fail(h, "null tensor pointer");
     if (A > 65535) return fail(h, "too many agents for one update launch (%lld)", (long long)A);
-    dim3 grid((unsigned)nchunk, (unsigned)A);
-    k_update_partial<<<grid, kUpdChunk, 0, (cudaStream_t)stream>>>(new_pos, t, T, prob_st_0, h->d_upd, S, nchunk, h->plans[t].std[0],
-                                                                  h->plans[t].std[1]);
-    k_update_write<<<grid, kUpdChunk, 0, (cudaStream_t)stream>>>(new_pos, t, T, prob_st_0, ldjs, normalizer, h->d_upd, prob_st_t, S, nchunk,
-                                                                h->plans[t].std[0], h->plans[t].std[1]);
-    h->launches += 2;
+    // one cluster of kUpdCluster CTAs per agent; a CTA keeps exp(base_lp') of its samples in shared memory
+    const long long chunk = ((S + kUpdCluster - 1) / kUpdCluster + 3) / 4 * 4;
+    const size_t smem = (size_t)chunk * sizeof(float);
+    if (smem + 1024 > (size_t)h->smem_optin) return fail(h, "too many samples per agent for the update kernel (%lld)", (long long)S);
+    const int per = (T - t) * 3;
+    const unsigned long long magic = ((1ull << 40) + per - 1) / per;
+    auto kern = lazy ? k_update<true> : k_update<false>;
+    if (smem > 48 * 1024) FC_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(kUpdCluster, (unsigned)A, 1);
+    cfg.blockDim = dim3(kUpdThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kUpdCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    FC_CUDA(h, cudaLaunchKernelEx(&cfg, kern, new_pos, t, T, prob_st_0, ldjs, normalizer, out, (long long)S, (int)chunk,
+                                  h->plans[t].std[0], h->plans[t].std[1], magic));
+    h->launches += 1;
     FC_CUDA(h, cudaGetLastError());
     return 0;
+}
+
+extern "C" int fc_update(fc_handle* h, const float* new_pos, int t, const float* prob_st_0, const float* ldjs,
+                         const float* normalizer, float* prob_st_t, int64_t A, int64_t S, void* stream) {
+    return update_impl(h, new_pos, t, prob_st_0, ldjs, normalizer, prob_st_t, A, S, stream, false);
+}
+
+extern "C" int fc_update_lazy(fc_handle* h, const float* new_pos, int t, const float* prob_st_0, const float* normalizer,
+                              float* base_lp_t, int64_t A, int64_t S, void* stream) {
+    return update_impl(h, new_pos, t, prob_st_0, nullptr, normalizer, base_lp_t, A, S, stream, true);
 }
 
 extern "C" int fc_tc_gemm_selftest(const float* A, const float* B, float* D, int N, int K, int device, int mode) {

@@ -599,70 +599,94 @@ __global__ void k_base_normalizer(const float* __restrict__ base_lp, float* __re
     if (threadIdx.x == 0) norm[blockIdx.x] = acc;
 }
 
-// Rapid update, two streaming passes over an (agents x sample-chunks) grid so that ONE agent (the reference's only
-// working case, B = 1) already spreads over ~40 SMs:
-//   pass 1: partial[a][c] = sum over the chunk's samples of exp(base log-prob at the newest observed position)
-//   pass 2: total = sum_c partial[a][c] (fixed order -> deterministic), per-sample log(bp / total * normalizer) into
-//           shared memory, then a flat, coalesced copy of prob_st_0[:, :, t:] with the log-prob column replaced by
-//           lp'[s] + ldjs[s, t+j].
-constexpr int kUpdChunk = 256;      // samples per CTA
+// Rapid update: ONE launch, one thread-block CLUSTER of kUpdCluster CTAs per agent (so that one agent -- the reference's
+// only working case, B = 1 -- already spreads over 8 SMs and 1000 agents fill the chip 8000 CTAs deep):
+//   phase 1: every CTA evaluates bp[s] = exp(base log-prob of its samples at the newest observed position) ONCE, keeps
+//            it in shared memory and block-reduces its partial sum;
+//   exchange: the partial sums are read from the peers' shared memory (DSMEM) in rank order -> deterministic total;
+//   phase 2: lp'[s] = log(bp / total * normalizer) in place, then either (full) a flat, coalesced copy of
+//            prob_st_0[:, :, t:] with the log-prob column replaced by lp'[s] + ldjs[s, t+j] -- 8 independent loads in
+//            flight per thread, no partial-sum round trip through HBM, no second pass over the positions -- or (lazy)
+//            just lp'(A, S): 40 KB per agent instead of 1.3 MB, for consumers that add ldjs themselves.
+constexpr int kUpdCluster = 8;
+constexpr int kUpdThreads = 256;
 
-__global__ void __launch_bounds__(kUpdChunk)
-k_update_partial(const float* __restrict__ new_pos, int t, int T, const float* __restrict__ prob0, float* __restrict__ partial,
-                 long long S, int nchunk, float sd0, float sd1) {
-    __shared__ float red[32];
-    const long long ag = blockIdx.y;
-    const long long s = (long long)blockIdx.x * kUpdChunk + threadIdx.x;
-    float v = 0.0f;
-    if (s < S) {
-        const float* q = prob0 + ((ag * S + s) * T + (t - 1)) * 3;
-        v = expf(normal_lp2(__ldg(q), __ldg(q + 1), __ldg(new_pos + ag * 2), __ldg(new_pos + ag * 2 + 1), sd0, sd1));
-    }
-    v = block_sum(v, red);
-    if (threadIdx.x == 0) partial[ag * nchunk + blockIdx.x] = v;
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem_f32(const float* local_ptr, uint32_t rank) {
+    uint32_t la = (uint32_t)__cvta_generic_to_shared(local_ptr), ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+    return v;
 }
 
-__global__ void __launch_bounds__(kUpdChunk)
-k_update_write(const float* __restrict__ new_pos, int t, int T, const float* __restrict__ prob0, const float* __restrict__ ldjs,
-               const float* __restrict__ normalizer, const float* __restrict__ partial, float* __restrict__ out, long long S,
-               int nchunk, float sd0, float sd1) {
-    __shared__ float lp_new[kUpdChunk];
+// chunk = samples per CTA (multiple of 4); dynamic shared memory: chunk floats.  per_magic = ceil(2^40 / per).
+template <bool LAZY>
+__global__ void __launch_bounds__(kUpdThreads)
+k_update(const float* __restrict__ new_pos, int t, int T, const float* __restrict__ prob0, const float* __restrict__ ldjs,
+         const float* __restrict__ normalizer, float* __restrict__ out, long long S, int chunk, float sd0, float sd1,
+         unsigned long long per_magic) {
+    extern __shared__ __align__(16) float upd_bp[];          // bp, then lp', of this CTA's samples
+    __shared__ float red[32];
+    __shared__ float my_partial;
     const long long ag = blockIdx.y;
-    const long long s0 = (long long)blockIdx.x * kUpdChunk;
-    float total = 0.0f;
-    for (int c = 0; c < nchunk; ++c) total += __ldg(partial + ag * nchunk + c);
-    const float nz = __ldg(normalizer + ag);
-    {
-        const long long s = s0 + threadIdx.x;
-        float lp = 0.0f;
-        if (s < S) {     // recomputed, not cached: the strided position read is an L2 hit for the flat copy below (a cached
-                         // exp(base_lp') array measured 8 % slower)
-            const float* q = prob0 + ((ag * S + s) * T + (t - 1)) * 3;
-            const float bp = expf(normal_lp2(__ldg(q), __ldg(q + 1), __ldg(new_pos + ag * 2), __ldg(new_pos + ag * 2 + 1), sd0, sd1));
-            lp = logf(bp / total * nz);       // same order of operations as fastpredNF.py:154-155
-        }
-        lp_new[threadIdx.x] = lp;
+    const uint32_t rank = cluster_ctarank();
+    const long long s0 = (long long)rank * chunk;
+    const int ns = (int)(S - s0 < (long long)chunk ? (S - s0 > 0 ? S - s0 : 0) : chunk);
+    const float np0 = __ldg(new_pos + ag * 2), np1 = __ldg(new_pos + ag * 2 + 1);
+    float acc = 0.0f;
+    for (int sl = threadIdx.x; sl < ns; sl += kUpdThreads) {
+        const float* q = prob0 + ((ag * S + s0 + sl) * T + (t - 1)) * 3;        // strided: 8 of every 36 T bytes
+        const float px = __ldg(q), py = __ldg(q + 1);
+        const float v = expf(normal_lp2(px, py, np0, np1, sd0, sd1));
+        upd_bp[sl] = v;
+        acc += v;
     }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) my_partial = acc;
+    cluster_sync_all();
+    float total = 0.0f;
+#pragma unroll
+    for (int r = 0; r < kUpdCluster; ++r) total += ld_dsmem_f32(&my_partial, (uint32_t)r);     // rank order: deterministic
+    cluster_sync_all();                                       // no CTA may exit (or reuse my_partial) while peers still read it
+    const float nz = __ldg(normalizer + ag);
+    for (int sl = threadIdx.x; sl < ns; sl += kUpdThreads) {
+        const float lp = logf(upd_bp[sl] / total * nz);       // same order of operations as fastpredNF.py:154-155
+        if (LAZY) out[ag * S + s0 + sl] = lp;
+        else upd_bp[sl] = lp;
+    }
+    if (LAZY) return;
     __syncthreads();
     const int Tt = T - t, per = Tt * 3;
-    const long long ns = (S - s0) < kUpdChunk ? (S - s0) : kUpdChunk;
-    const float* src = prob0 + (ag * S + s0) * T * 3;
-    const float* lj = ldjs + (ag * S + s0) * T;
+    const float* src = prob0 + ((ag * S + s0) * T + t) * 3;   // sample sl's tail row block starts at src + sl * 3T
+    const float* lj = ldjs + (ag * S + s0) * T + t;
     float* dst = out + (ag * S + s0) * per;
-    // flat element index e = sl * per + r walked without divisions: e advances by the block size every iteration
-    const int nelem = (int)ns * per;
-    const int dq = kUpdChunk / per, dr = kUpdChunk - dq * per;
-    int sl = threadIdx.x / per, r = threadIdx.x - sl * per;
-#pragma unroll 4
-    for (int e = threadIdx.x; e < nelem; e += kUpdChunk) {
-        const int j = (r * 43) >> 7, c = r - j * 3;            // r / 3 for r < 48 (per <= 3 * 15)
-        const int row = sl * T + t + j;
-        float v;
-        if (c < 2) v = __ldg(src + row * 3 + c);
-        else v = lp_new[sl] + __ldg(lj + row);
-        dst[e] = v;
-        sl += dq; r += dr;
-        if (r >= per) { r -= per; ++sl; }
+    const int nelem = ns * per, T3 = 3 * T;
+    constexpr int U = 8;
+    for (int e0 = threadIdx.x; e0 < nelem; e0 += U * kUpdThreads) {
+        float v[U];
+        int sls[U];
+        bool isl[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int e = e0 + k * kUpdThreads;
+            const int ec = e < nelem ? e : nelem - 1;
+            const int sl = (int)(((unsigned long long)(unsigned)ec * per_magic) >> 40);     // ec / per
+            const int r = ec - sl * per;
+            const int j = (r * 43) >> 7, c = r - j * 3;                                    // r / 3 for r < 128
+            sls[k] = sl;
+            isl[k] = c == 2;
+            const float* p = c == 2 ? lj + sl * T + j : src + sl * T3 + r;
+            v[k] = __ldg(p);
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int e = e0 + k * kUpdThreads;
+            if (e < nelem) dst[e] = isl[k] ? upd_bp[sls[k]] + v[k] : v[k];
+        }
     }
 }
 

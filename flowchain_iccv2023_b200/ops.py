@@ -253,3 +253,25 @@ def update(hid: int, new_pos: torch.Tensor, time_step: int, prob_st_0: torch.Ten
 def _(hid, new_pos, time_step, prob_st_0, ldjs, normalizer):
     A, S, T, _ = prob_st_0.shape
     return prob_st_0.new_empty((A, S, T - time_step, 3))
+
+
+@torch.library.custom_op("flowchain::update_lazy", mutates_args=())
+def update_lazy(hid: int, new_pos: torch.Tensor, time_step: int, prob_st_0: torch.Tensor,
+                normalizer: torch.Tensor) -> torch.Tensor:
+    """base_lp_t (A, S): the per-sample term of the rapid update; prob_st_t[..., 2] == base_lp_t[..., None] + ldjs[:, :, t:]."""
+    h = _h(hid)
+    T = h.spec.pred_len
+    A, S = prob_st_0.shape[0], prob_st_0.shape[1]
+    if not (0 < time_step < T):
+        raise AssertionError(f"time_step for update need to be 0~{T - 1}, got {time_step}")
+    out = torch.empty((A, S), dtype=torch.float32, device=prob_st_0.device)
+    rc = _lib.load().fc_update_lazy(
+        h.ptr, _chk(new_pos, (A, 2), "new_pos", h), time_step, _chk(prob_st_0, (A, S, T, 3), "prob_st_0", h),
+        _chk(normalizer.reshape(-1), (A,), "normalizer", h), out.data_ptr(), A, S, _stream(h))
+    h.check(rc, "fc_update_lazy")
+    return out
+
+
+@update_lazy.register_fake
+def _(hid, new_pos, time_step, prob_st_0, normalizer):
+    return prob_st_0.new_empty((prob_st_0.shape[0], prob_st_0.shape[1]))

@@ -8,7 +8,11 @@
  * Conventions
  *  - every data pointer is a DEVICE pointer to contiguous float32 unless stated otherwise; the
  *    caller owns all buffers; calls enqueue on `stream` (a cudaStream_t passed as void*), never
- *    synchronise, and are CUDA-graph capturable;
+ *    synchronise, and are CUDA-graph capturable.  Two documented exceptions: fc_load_weights (one-off,
+ *    synchronises `stream`), and the FIRST fc_grid_log_prob call with a K that is not a power of two <= 32 at a
+ *    new (larger) size, which grows a handle-owned staging buffer (it returns an error instead when `stream`
+ *    is being captured: run it once outside the capture);
+ *  - calls run on the handle's device and restore the caller's current device before returning;
  *  - return value 0 = ok, non-zero = error; message via fc_last_error(); no C++ exceptions cross;
  *  - a handle is thread-compatible (one caller at a time); distinct handles are independent;
  *  - noise: `eps` (and `z0`) inject the CIF auxiliary draws (noise tape, layouts below); when
@@ -44,14 +48,21 @@ typedef struct fc_model_desc {
 
 /* arithmetic path of the conditioner / auxiliary-density MLPs */
 enum { FC_PREC_FP32 = 0,    /* CUDA-core fp32, parity 1e-4 (+rel) nats                                         */
-       FC_PREC_BF16 = 1,    /* tcgen05, bf16 operands / fp32 accumulate, single pass: fast, ~1e-1 nats           */
+       FC_PREC_BF16 = 1,    /* RETIRED (single-pass bf16 operands, ~1e-1 nats, failed the 5e-3 bar): every call returns an
+                               error naming FC_PREC_F16 / FC_PREC_F16X3; the value is kept so the numbering is stable       */
        FC_PREC_F16X3 = 2,   /* tcgen05, split-fp16 operands (a_hi+a_lo)(W_hi+W_lo), 3 MMA passes, fp32 accumulate:
                                fp32-grade, meets the 5e-3 nats tensor-core parity bar                             */
        FC_PREC_F16 = 3 };   /* tcgen05, fp16 operands / fp32 accumulate, single pass: ~3e-2 nats                  */
 /* Coverage: FC_PREC_FP32 every entry point and model shape.  FC_PREC_F16X3 / FC_PREC_F16: fc_log_prob,
- * fc_log_prob_sequential, fc_grid_log_prob[_multicast] (per-step and chain) and fc_sample_with_log_prob, for
- * hidden_size % 16 == 0, hidden_size <= 96 (chain / sampler <= 80) and 2*(cond_size + 2*pred_len) <= 96; other shapes
- * return an error that names FC_PREC_FP32.  FC_PREC_BF16: per-step density only. */
+ * fc_log_prob_sequential, fc_grid_log_prob[_multicast] (per-step and chain) and fc_sample_with_log_prob for
+ * hidden_size % 16 == 0 and an even cond_size, on one of two kernels chosen at fc_load_weights:
+ *   - every layer <= 80 wide (hidden_size <= 80 and 2*(cond_size + 2*pred_len) <= 80, e.g. the default ETH model):
+ *     two resident 128-row tiles per CTA (csrc/kernels_tc3.cuh);
+ *   - wider, up to hidden_size 256 / cond_size 64 (BASELINE config 5, the reference's tuning range
+ *     src/main.py:222-229), as long as  max(hidden_size, W) + pad16(C) + 2*pad16(C + 2) <= 512  tensor-memory columns
+ *     with C = cond_size + 2*(pred_len - 1), W = pad16(2*(C + 2)): one tile per CTA, K-slab weight streaming
+ *     (csrc/kernels_tcw.cuh);
+ * other shapes return an error that names FC_PREC_FP32. */
 
 /* prefix modes of the dense-grid evaluation */
 enum { FC_PREFIX_SELF = 0,     /* x[:, i] = g for every step (the literal reference call)   */
@@ -96,7 +107,7 @@ int fc_grid_log_prob(fc_handle* h, const float* base_pos, const float* cond, con
 
 /* Multi-GPU variant of fc_grid_log_prob (K = 1): `out_multicast` is the NVSwitch MULTICAST address of a symmetric
  * buffer (cuMulticast* / torch symmetric memory), offset to this rank's block of the global (A_total, T, G) maps.
- * The kernel's ordinary 4-byte result stores (system scope) are replicated to every peer by the switch, i.e. the
+ * The kernel's 4-byte result stores (multimem.st, system scope) are replicated to every peer by the switch, i.e. the
  * all-gather that the reference-side wrapper would run after the density evaluation (one ncclAllGather)
  * is performed by the stores themselves, tile by tile, with no second kernel.  The caller runs one cross-rank barrier
  * before reading the maps.  Replaces: flow.log_prob over rows = A*G (fastpredNF.py:450-465) + the all-gather. */
@@ -123,6 +134,12 @@ int fc_base_normalizer(fc_handle* h, const float* base_lp, float* normalizer, in
  * -> prob_st_t (A,S,T-t,3).  0 < time_step < T. */
 int fc_update(fc_handle* h, const float* new_pos, int time_step, const float* prob_st_0, const float* ldjs,
               const float* normalizer, float* prob_st_t, int64_t A, int64_t S, void* stream);
+
+/* Lazy variant of fc_update for consumers that add `ldjs` themselves (the only form whose HBM
+ * traffic allows < 100 us per 1000-agent batch): writes ONLY base_lp_t (A,S) = log(bp / sum_s bp * normalizer), the
+ * per-sample term that fastpredNF.py:150-156 adds to ldjs_tmp[:, :, t:]; prob_st_t[a,s,j,2] == base_lp_t[a,s] + ldjs[a,s,t+j]. */
+int fc_update_lazy(fc_handle* h, const float* new_pos, int time_step, const float* prob_st_0, const float* normalizer,
+                   float* base_lp_t, int64_t A, int64_t S, void* stream);
 
 /* Diagnostic: D[128 x N] = A[128 x K] * B[N x K]^T on the tcgen05 tensor cores (bf16 operands, fp32
  * accumulate) through the same descriptor / TMEM / mbarrier helpers the fused kernel uses.  HOST pointers,

@@ -255,3 +255,86 @@ def test_wrapper_grid_and_gt_log_prob(flows):
     np.testing.assert_allclose(ps[0, :, 0, :2], grid, atol=1e-6)
     ref = orc.grid_log_prob_self(p, g["base_pos"][:B], g["cond"][:B], grid, eps_g, np.float64)
     assert_close32(ps[..., 2], ref, "predict_forward")
+
+
+def _update_caches(f, spec, A, S, seed):
+    """Sampler caches for the rapid update, produced on the GPU (tensor-core sampler when the shape allows it)."""
+    from flowchain_iccv2023_b200 import _lib
+    inp = synth.make_inputs(spec, A, seed=seed)
+    bp, cd = T(inp["base_pos"]), T(inp["cond"])
+    h = f.engine()
+    seq, lp, ldjs, base = torch.ops.flowchain.sample_with_log_prob(h.id, bp, cd, S, None, None, seed + 1, _lib.FC_PREC_F16X3)
+    prob0 = torch.cat([seq, lp[..., None]], dim=-1).contiguous()
+    norm = torch.ops.flowchain.base_normalizer(h.id, base.contiguous())
+    new_pos = (bp + 0.05 * torch.from_numpy(synth.normal(seed + 2, "np", (A, 2)).astype(np.float32)).cuda()).contiguous()
+    return h, prob0, ldjs, norm, new_pos
+
+
+def _check_update(out, ref, what):
+    np.testing.assert_array_equal(out[..., :2], ref[..., :2])
+    fin = np.isfinite(ref[..., -1])
+    mism = fin != np.isfinite(out[..., -1])
+    assert mism.mean() < 1e-3, (what, mism.mean())               # -inf on underflow: only the threshold itself may differ
+    ok = fin & ~mism
+    # log(bp / total * nz): bp = exp(lp) carries |lp| * 6e-8 relative error, so the bar is stated on the base term
+    err = np.abs(out[..., -1][ok].astype(np.float64) - ref[..., -1][ok])
+    tol = 1e-4 + 3e-6 * np.abs(ref[..., -1][ok])
+    print(f"{what}: max|err| {err.max():.3e}  inside 1e-4+3e-6|ref| {np.mean(err <= tol):.6f}  -inf mismatches {mism.sum()}")
+    assert np.mean(err <= tol) > 0.999 and err.max() < 2e-3
+
+
+@pytest.mark.parametrize("t", [1, 6, 11])
+def test_update_config3_1000_agents(flows, t):
+    """BASELINE config 3 at full size: 1000 agents x 10 000 samples through fc_update (one cluster of 8 CTAs per agent)
+    against the vmap of the B = 1 reference call (oracle.predict_from_new_obs_batched, fp64) on the same caches, and the
+    lazy form against the same numbers."""
+    f, spec, p, g = flows("default_eth")
+    A, S = 1000, 10000
+    h, prob0, ldjs, norm, new_pos = _update_caches(f, spec, A, S, 900)
+    out = torch.ops.flowchain.update(h.id, new_pos, t, prob0, ldjs, norm)
+    assert out.shape == (A, S, spec.pred_len - t, 3)
+    lazy = torch.ops.flowchain.update_lazy(h.id, new_pos, t, prob0, norm)
+    assert lazy.shape == (A, S)
+    # bit-level consistency of the two forms: full[..., 2] == lazy + ldjs[:, :, t:]
+    assert torch.equal(out[..., 2], lazy[..., None] + ldjs[:, :, t:])
+    sel = np.r_[0:8, 500:504, 996:1000]                            # the oracle is a Python loop: check 16 agents in fp64
+    ref = orc.predict_from_new_obs_batched(p, prob0[sel].cpu().numpy(), ldjs[sel].cpu().numpy(), norm[sel, 0].cpu().numpy(),
+                                           new_pos[sel].cpu().numpy(), t, np.float64)
+    _check_update(out[sel].cpu().numpy(), ref, f"update A=1000 t={t}")
+    # every agent against a torch fp64 restatement of the same three lines (fastpredNF.py:150-156) on the device
+    pos = prob0[:, :, t - 1, :2].double()
+    std = torch.clamp(f.var[t].double(), min=1e-4)
+    lpb = (-((pos - new_pos[:, None].double()) ** 2) / (2 * std ** 2) - std.log() - 0.5 * np.log(2 * np.pi)).sum(-1)
+    bpb = lpb.exp()
+    ref_all = (bpb / bpb.sum(1, keepdim=True) * norm.double()).log()
+    fin = torch.isfinite(ref_all) & torch.isfinite(lazy)
+    err = (lazy.double() - ref_all)[fin].abs()
+    assert fin.float().mean() > 0.9 and err.max().item() < 2e-3
+    assert (err <= 1e-4 + 3e-6 * ref_all[fin].abs()).float().mean().item() > 0.999
+
+
+def test_update_ragged_and_graph_capture(flows):
+    """Sample counts that do not divide the cluster (S = 1, 7, 1001), one agent, and capture into a CUDA graph
+    (fc_update must not allocate or synchronise)."""
+    f, spec, p, g = flows("default_eth")
+    for A, S in ((1, 1), (3, 7), (2, 1001)):
+        h, prob0, ldjs, norm, new_pos = _update_caches(f, spec, A, S, 950 + S)
+        for t in (1, spec.pred_len - 1):
+            out = torch.ops.flowchain.update(h.id, new_pos, t, prob0, ldjs, norm).cpu().numpy()
+            ref = orc.predict_from_new_obs_batched(p, prob0.cpu().numpy(), ldjs.cpu().numpy(), norm[:, 0].cpu().numpy(),
+                                                   new_pos.cpu().numpy(), t, np.float64)
+            if S > 1:
+                _check_update(out, ref, f"update A={A} S={S} t={t}")
+            else:
+                np.testing.assert_allclose(out, ref, atol=1e-4, rtol=3e-6)
+    h, prob0, ldjs, norm, new_pos = _update_caches(f, spec, 4, 2048, 990)
+    eager = torch.ops.flowchain.update(h.id, new_pos, 3, prob0, ldjs, norm)
+    graph = torch.cuda.CUDAGraph()
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        with torch.cuda.graph(graph, stream=st):
+            cap = torch.ops.flowchain.update(h.id, new_pos, 3, prob0, ldjs, norm)
+    torch.cuda.synchronize()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(cap, eager)
