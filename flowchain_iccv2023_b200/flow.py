@@ -2,9 +2,11 @@
 
 Class, method and state_dict names follow the reference (src/models/TP/fastpredNF.py:380-826,
 src/models/TP/TFCondARFlow.py:254-402) so a reference checkpoint loads unchanged and callers
-(`fastpredNF_TP`, src/main.py) need no edits.  The modules only OWN the parameters; all
-arithmetic of the path runs in the fused sm_100a kernels behind ``torch.ops.flowchain.*``.
-There is no PyTorch/CPU fallback -- without the CUDA library every density call raises.
+(`fastpredNF_TP`, src/main.py) need no edits.  In eval() mode -- inference, the hot path -- the modules
+only OWN the parameters: all arithmetic runs in the fused sm_100a kernels behind ``torch.ops.flowchain.*``
+and there is no PyTorch/CPU fallback (without the CUDA library every density call raises).  In train()
+mode with grad enabled the same methods run the modules' plain differentiable PyTorch forwards instead
+(SURVEY §8b "Registration"): that is the reference's training path (`update()`), not an inference fallback.
 
 Noise: the reference draws ``torch.randn_like`` inside every CIF step (log_prob is stochastic,
 SURVEY §0 D7).  Here each call takes ``eps=`` (a noise tape, layouts in include/flowchain_b200.h)
@@ -24,15 +26,13 @@ from .synth import FlowSpec
 
 
 # ------------------------------------------------------------------------------------------------
-# parameter holders (same registration order / keys as the reference modules)
+# modules (same registration order / keys as the reference modules)
+#
+# Inference (module in eval() mode) never calls these forwards: all arithmetic of the path runs in the fused
+# sm_100a kernels.  They exist for the TRAINING path (SURVEY §8b "Registration": with grad enabled the accelerated
+# methods defer to the PyTorch modules so `update()` -- Adam on -log_prob, fastpredNF.py:186-202 -- keeps working):
+# plain differentiable PyTorch, used only when the flow is in train() mode with grad enabled.
 # ------------------------------------------------------------------------------------------------
-
-class _Fused(nn.Module):
-    def forward(self, *a, **k):
-        raise RuntimeError(
-            f"{type(self).__name__} only holds parameters: its arithmetic is fused into the flowchain CUDA "
-            "kernels -- call the flow's log_prob / log_prob_sequential / sample_with_log_prob instead")
-
 
 def _mlp(dims, act):
     layers = []
@@ -43,8 +43,8 @@ def _mlp(dims, act):
     return nn.Sequential(*layers)
 
 
-class LinearMaskedCoupling(_Fused):
-    """Parameters of the masked affine coupling (TFCondARFlow.py:336-358): mask, s_net (Tanh), t_net (ReLU)."""
+class LinearMaskedCoupling(nn.Module):
+    """Masked affine coupling (TFCondARFlow.py:336-402): mask, s_net (Tanh), t_net (ReLU); conditioner input [y, x*mask]."""
 
     def __init__(self, input_size, hidden_size, n_hidden, mask, cond_label_size):
         super().__init__()
@@ -54,9 +54,23 @@ class LinearMaskedCoupling(_Fused):
         self.t_net = _mlp(dims, nn.ReLU)
         self.t_net.load_state_dict(self.s_net.state_dict())   # the reference deep-copies s_net into t_net
 
+    def _st(self, kept, y):
+        free = 1 - self.mask
+        h = torch.cat([y, kept], dim=-1)
+        return torch.tanh(self.s_net(h)) * free, self.t_net(h) * free
 
-class BatchNorm(_Fused):
-    """Parameters of the invertible batch-norm layer (TFCondARFlow.py:275-284); eval statistics only."""
+    def forward(self, x, y):
+        log_s, t = self._st(x * self.mask, y)
+        return x * torch.exp(log_s) + t, log_s
+
+    def inverse(self, u, y):
+        log_s, t = self._st(u * self.mask, y)
+        return (u - t) * torch.exp(-log_s), -log_s
+
+
+class BatchNorm(nn.Module):
+    """Invertible batch-norm layer (TFCondARFlow.py:272-330).  train(): batch statistics (unbiased variance) and the
+    reference's running update `running <- 0.9 running + 0.1 batch`; eval(): running statistics."""
 
     def __init__(self, input_size, momentum=0.9, eps=1e-5):
         super().__init__()
@@ -66,25 +80,73 @@ class BatchNorm(_Fused):
         self.register_buffer("running_mean", torch.zeros(input_size))
         self.register_buffer("running_var", torch.ones(input_size))
 
+    def _stats(self, x=None):
+        if not self.training:
+            return self.running_mean, self.running_var
+        if x is not None:
+            flat = x.reshape(-1, x.shape[-1])
+            self.batch_mean, self.batch_var = flat.mean(0), flat.var(0)
+            with torch.no_grad():
+                self.running_mean.mul_(self.momentum).add_(self.batch_mean.detach() * (1 - self.momentum))
+                self.running_var.mul_(self.momentum).add_(self.batch_var.detach() * (1 - self.momentum))
+        return self.batch_mean, self.batch_var
+
+    def forward(self, x, y=None):
+        mean, var = self._stats(x)
+        out = torch.exp(self.log_gamma) * (x - mean) / torch.sqrt(var + self.eps) + self.beta
+        return out, (self.log_gamma - 0.5 * torch.log(var + self.eps)).expand_as(x)
+
+    def inverse(self, out, y=None):
+        mean, var = self._stats(None)
+        x = (out - self.beta) * torch.exp(-self.log_gamma) * torch.sqrt(var + self.eps) + mean
+        return x, (0.5 * torch.log(var + self.eps) - self.log_gamma).expand_as(out)
+
 
 class FlowSequential(nn.Sequential):
-    """Container [coupling, BN] x n_blocks (TFCondARFlow.py:254)."""
+    """Container [coupling, BN] x n_blocks (TFCondARFlow.py:254-269): per-dim log-dets summed over modules, then over dims."""
 
-    def forward(self, *a, **k):
-        return _Fused.forward(self)
+    def forward(self, x, y):
+        total = 0
+        for module in self:
+            x, ldj = module(x, y)
+            total = total + ldj
+        return x, total.sum(-1)
+
+    def inverse(self, u, y):
+        total = 0
+        for module in reversed(self):
+            u, ldj = module.inverse(u, y)
+            total = total + ldj
+        return u, total.sum(-1)
 
 
-class DiagonalGaussianConditionalDensity(_Fused):
-    """Parameters of r(u|z,y) / q(u|w,y) (fastpredNF.py:690-699)."""
+_LOG_2PI = 1.8378770664093453
+
+
+class DiagonalGaussianConditionalDensity(nn.Module):
+    """r(u|z,y) / q(u|w,y) (fastpredNF.py:690-733): diagonal Gaussian whose mean / log-std come from two MLPs."""
 
     def __init__(self, cond_dim, out_dim):
         super().__init__()
         self.shift_net = _mlp([cond_dim, 2 * cond_dim, 2 * cond_dim, out_dim], nn.ReLU)
         self.log_scale_net = _mlp([cond_dim, 2 * cond_dim, 2 * cond_dim, out_dim], nn.ReLU)
 
+    @staticmethod
+    def _lp(u, mean, log_std):
+        return -0.5 * u.shape[-1] * _LOG_2PI - log_std.sum(-1) - 0.5 * ((u - mean) ** 2 / torch.exp(log_std) ** 2).sum(-1)
 
-class CIF_step(_Fused):
-    """One continuously-indexed flow step (fastpredNF.py:756-767)."""
+    def log_prob(self, u, cond_inputs):
+        return self._lp(u, self.shift_net(cond_inputs), self.log_scale_net(cond_inputs))
+
+    def sample(self, cond_inputs, eps=None):
+        mean, log_std = self.shift_net(cond_inputs), self.log_scale_net(cond_inputs)
+        eps = torch.randn_like(mean) if eps is None else eps
+        u = torch.exp(log_std) * eps + mean
+        return u, self._lp(u, mean, log_std)
+
+
+class CIF_step(nn.Module):
+    """One continuously-indexed flow step (fastpredNF.py:756-781), K = 1 auxiliary sample."""
 
     def __init__(self, bijection, input_size, cond_label_size):
         super().__init__()
@@ -92,6 +154,16 @@ class CIF_step(_Fused):
         self.cond_label_size = cond_label_size
         self.r_u_given_z = DiagonalGaussianConditionalDensity(input_size + cond_label_size, cond_label_size)
         self.q_u_given_w = DiagonalGaussianConditionalDensity(input_size + cond_label_size, cond_label_size)
+
+    def forward(self, z, y, eps=None):
+        u, log_r = self.r_u_given_z.sample(torch.cat([z, y], dim=-1), eps)
+        w, ldj = self.bijection(z, u)
+        return w, ldj + self.q_u_given_w.log_prob(u, torch.cat([w, y], dim=-1)) - log_r
+
+    def inverse(self, w, y, eps=None):
+        u, log_q = self.q_u_given_w.sample(torch.cat([w, y], dim=-1), eps)
+        z, ldj = self.bijection.inverse(w, u)
+        return z, ldj + log_q - self.r_u_given_z.log_prob(u, torch.cat([z, y], dim=-1))
 
 
 def create_RealNVP_step(n_blocks, input_size, hidden_size, n_hidden, cond_label_size):
@@ -186,31 +258,40 @@ class fastpredNF_CIF_separate_cond(nn.Module):
         """fastpredNF.base_dist (fastpredNF.py:401-402)."""
         return Normal(base_pos, torch.clamp(self.var[step], min=1e-4))
 
-    @torch.no_grad()
     def log_prob(self, base_pos, x, cond, eps=None, seed=None, precision=None):
         """flow.log_prob == log_prob_separate (fastpredNF.py:450-452, 460-465): (N,2),(N,T,2),(N,T,C0) -> (N,T)."""
-        h = self.engine()
-        src = x.device
-        out = torch.ops.flowchain.log_prob(
-            h.id, self._dev(base_pos), self._dev(x), self._dev(cond), self._dev(eps),
-            0 if eps is not None else self._seed(seed), self.precision if precision is None else precision)
-        return out.to(src)
+        if self._training_path():
+            return self._log_prob_separate_torch(base_pos, x, cond, eps)
+        with torch.no_grad():
+            h = self.engine()
+            src = x.device
+            out = torch.ops.flowchain.log_prob(
+                h.id, self._dev(base_pos), self._dev(x), self._dev(cond), self._dev(eps),
+                0 if eps is not None else self._seed(seed), self.precision if precision is None else precision)
+            return out.to(src)
 
     log_prob_separate = log_prob
 
-    @torch.no_grad()
     def log_prob_sequential(self, base_pos, x, cond, n_step=None, eps=None, seed=None, precision=None):
         """fastpredNF.log_prob_sequential (fastpredNF.py:454-458): full chain, (N,T) or (N,n_step+1)."""
-        h = self.engine()
-        src = x.device
-        out = torch.ops.flowchain.log_prob_sequential(
-            h.id, self._dev(base_pos), self._dev(x), self._dev(cond), self._dev(eps),
-            0 if eps is not None else self._seed(seed), -1 if n_step is None else int(n_step),
-            self.precision if precision is None else precision)
-        return out.to(src)
+        if self._training_path():
+            return self._log_prob_sequential_torch(base_pos, x, cond, n_step, eps)
+        with torch.no_grad():
+            h = self.engine()
+            src = x.device
+            out = torch.ops.flowchain.log_prob_sequential(
+                h.id, self._dev(base_pos), self._dev(x), self._dev(cond), self._dev(eps),
+                0 if eps is not None else self._seed(seed), -1 if n_step is None else int(n_step),
+                self.precision if precision is None else precision)
+            return out.to(src)
 
-    @torch.no_grad()
     def sample_with_log_prob(self, base_pos, cond, z0=None, eps=None, seed=None, precision=None):
+        if self._training_path():
+            return self._sample_with_log_prob_torch(base_pos, cond, z0, eps)
+        with torch.no_grad():
+            return self._sample_with_log_prob_cuda(base_pos, cond, z0, eps, seed, precision)
+
+    def _sample_with_log_prob_cuda(self, base_pos, cond, z0=None, eps=None, seed=None, precision=None):
         """fastpredNF.sample_with_log_prob (fastpredNF.py:472-477).
 
         Accepts the reference's expanded arguments base_pos (B,S,2), cond (B,S,T,C0) (stride-0
@@ -304,4 +385,81 @@ class fastpredNF_CIF_separate_cond(nn.Module):
             self.precision if precision is None else precision)
 
     def forward(self, *a, **k):
-        return _Fused.forward(self)
+        raise RuntimeError("call log_prob / log_prob_sequential / sample_with_log_prob / grid_log_prob")
+
+    # -- training path: the modules' plain differentiable PyTorch forwards ---------------------------------------------
+    def _training_path(self) -> bool:
+        """train() mode with grad enabled = the reference's eager training path (what `update()` differentiates).
+        eval() mode always runs the fused kernels and raises without a B200: there is no CPU inference fallback."""
+        return self.training and torch.is_grad_enabled()
+
+    def forward_separate(self, seq, cond, eps=None):
+        """fastpredNF_separate_cond.forward_separate (fastpredNF.py:571-584): teacher-forced per-step transform.
+        seq (N,T,2), cond (N,T,C0), eps (N, sum_i C_i) | None -> u (N,T,2), ldj (N,T)."""
+        N, T = seq.shape[0], seq.shape[1]
+        flat = seq.reshape(N, T * self.input_size)
+        us, ldjs, off = [], [], 0
+        for i, net in enumerate(self.net):
+            C = self.spec.cond_width(i)
+            y = torch.cat([cond[:, i], flat[:, :i * self.input_size]], dim=-1)
+            u, l = net(seq[:, i], y, None if eps is None else eps[:, off:off + C])
+            off += C
+            us.append(u)
+            ldjs.append(l)
+        return torch.stack(us, dim=1), torch.stack(ldjs, dim=1)
+
+    def forward_sequential(self, seq, cond, n_step=None, eps=None):
+        """fastpredNF_separate_cond.forward_sequential (fastpredNF.py:548-569): result index j carries
+        net[0] o ... o net[j] (seq[:, j]); ldj_j = mean over its chain steps.  eps: the sequential tape layout."""
+        N, T, D = seq.shape[0], seq.shape[1], self.input_size
+        flat = seq.reshape(N, 1, T * D)
+        x, cum = seq[:, -1:], 0
+        offs, o = [], 0
+        for k in range(T):
+            offs.append(o)
+            o += (T - k) * self.spec.cond_width(k)
+        last = -1 if n_step is None else T - 1 - n_step
+        for step in range(T - 1, last, -1):
+            C = self.spec.cond_width(step)
+            y = torch.cat([cond[:, step:], flat[..., :step * D].expand(N, T - step, step * D)], dim=-1)
+            e = None if eps is None else eps[:, offs[step]:offs[step] + (T - step) * C].reshape(N, T - step, C)
+            x, l = self.net[step](x, y, e)
+            cum = cum + l
+            if step != 0:
+                x = torch.cat([seq[:, step - 1:step], x], dim=1)
+                cum = torch.cat([torch.zeros_like(cum[:, :1]), cum], dim=1)
+        return x, cum / torch.arange(1, cum.shape[1] + 1, device=cum.device, dtype=cum.dtype)
+
+    def inverse(self, u, cond, eps=None):
+        """fastpredNF_separate_cond.inverse (fastpredNF.py:586-607): autoregressive sampling direction.
+        u (..., 2), cond (..., T, C0) -> seq (..., T, 2), running mean of the step terms (..., T), step terms (..., T)."""
+        seq, ldjs, off = [], [], 0
+        lead = u.shape[:-1]
+        for step, net in enumerate(self.net):
+            C = self.spec.cond_width(step)
+            y = cond[..., step, :]
+            if step:
+                y = torch.cat([y, torch.stack(seq, dim=-2).reshape(*lead, -1)], dim=-1)
+            u, l = net.inverse(u, y, None if eps is None else eps[..., off:off + C])
+            off += C
+            seq.append(u)
+            ldjs.append(l)
+        ldjs = torch.stack(ldjs, dim=-1)
+        counts = torch.arange(1, ldjs.shape[-1] + 1, device=ldjs.device, dtype=ldjs.dtype)
+        return torch.stack(seq, dim=-2), torch.cumsum(ldjs, dim=-1) / counts, ldjs
+
+    def _log_prob_separate_torch(self, base_pos, x, cond, eps=None):
+        u, ldj = self.forward_separate(x, cond, eps)
+        prev = torch.cat([base_pos[:, None], x[:, :-1]], dim=1)
+        return self.base_dist(prev, list(range(prev.shape[1]))).log_prob(u).sum(-1) + ldj
+
+    def _log_prob_sequential_torch(self, base_pos, x, cond, n_step=None, eps=None):
+        u, ldj = self.forward_sequential(x, cond, n_step, eps)
+        return self.base_dist(base_pos[:, None]).log_prob(u).sum(-1) + ldj
+
+    def _sample_with_log_prob_torch(self, base_pos, cond, z0=None, eps=None):
+        dist = self.base_dist(base_pos)
+        u0 = dist.sample() if z0 is None else z0.reshape(base_pos.shape) * dist.scale + dist.loc
+        seq, cum, ldjs = self.inverse(u0, cond, None if eps is None else eps.reshape(*base_pos.shape[:-1], -1))
+        base = dist.log_prob(u0).sum(-1, keepdim=True)
+        return seq, base + cum, ldjs, base

@@ -7,7 +7,8 @@ Kept: ``predict(data_dict, return_prob)``, ``predict_from_new_obs(data_dict, tim
 (``ldjs_tmp``, ``base_prob_normalizer_tmp``).  Added: a working ``predict_forward`` (dense grid).
 The history encoder is NOT part of this path (north_star (d)): pass any callable
 ``encoder(data_dict) -> (B, T, C0)`` (a PyTorch module in production, a stub in tests/bench).
-``update()`` (the Adam training step) is out of scope for this tier and raises.
+``update()`` is the reference's Adam training step on the flow's differentiable PyTorch path
+(flow.py, train() mode); the fused kernels re-pack the weights automatically afterwards.
 """
 from __future__ import annotations
 
@@ -23,9 +24,13 @@ from .flow import fastpredNF_CIF_separate_cond
 class fastpredNF_TP(nn.Module):
     def __init__(self, cfg=None, encoder: Optional[Callable] = None, pred_len: int = 12, obs_len: int = 8,
                  pred_state: str = "state_v", n_blocks: int = 3, n_hidden: int = 2, hidden_size: int = 64,
-                 cond_size: int = 16, output_path: Optional[str] = None):
+                 cond_size: int = 16, output_path: Optional[str] = None, lr: float = 1e-3, weight_decay: float = 0.0,
+                 dequantize: bool = False):
         super().__init__()
         if cfg is not None:   # duck-typed yacs node (src/default_params.py)
+            lr = cfg.SOLVER.LR
+            weight_decay = cfg.SOLVER.WEIGHT_DECAY
+            dequantize = cfg.SOLVER.DEQUANTIZE
             pred_len = cfg.DATA.PREDICT_LENGTH
             obs_len = cfg.DATA.OBSERVE_LENGTH
             pred_state = cfg.DATA.TP.PRED_STATE
@@ -41,6 +46,8 @@ class fastpredNF_TP(nn.Module):
         self.flow = fastpredNF_CIF_separate_cond(input_size=2, n_blocks=n_blocks, n_hidden=n_hidden,
                                                  hidden_size=hidden_size, cond_label_size=cond_size,
                                                  flow_architecture="realNVP", pred_len=pred_len)
+        self.lr, self.weight_decay, self.dequantize = lr, weight_decay, dequantize
+        self.optimizer = None            # built on first use so that an nn.Module encoder assigned later is included
         self.optimizers = []
         self.sample_num_prob = 10000     # fastpredNF.py:104
         self.sample_num_ml = 100         # fastpredNF.py:126
@@ -139,10 +146,35 @@ class fastpredNF_TP(nn.Module):
         base_pos = self.get_base_pos(data_dict)
         return self.flow.log_prob(base_pos, data_dict["gt_st"], dist_args, **kw)
 
+    def build_optimizer(self):
+        """Adam with weight decay on everything but biases (fastpredNF.py:72-89)."""
+        named = list(self.named_parameters())
+        groups = [{"params": [p for n, p in named if "bias" not in n], "weight_decay": self.weight_decay},
+                  {"params": [p for n, p in named if "bias" in n], "weight_decay": 0.0}]
+        self.optimizer = torch.optim.Adam(groups, self.lr)
+        self.optimizers = [self.optimizer]
+        return self.optimizer
+
     def update(self, data_dict: Dict) -> Dict:
-        raise NotImplementedError(
-            "fastpredNF_TP.update is the Adam training step (fastpredNF.py:186-202); training stays on the "
-            "reference PyTorch modules and is out of scope of the B200 density path (SURVEY §3.4)")
+        """Training step (fastpredNF.py:186-202): Adam on the mean negative per-step log-density of the ground-truth
+        future.  Runs the flow's differentiable PyTorch path (flow.py); BatchNorm uses batch statistics in train() mode
+        exactly as the reference's layer does.  The packed weights of the fused kernels are re-built on the next
+        inference call."""
+        if self.optimizer is None:
+            self.build_optimizer()
+        with torch.enable_grad():
+            dist_args = self.encoder(data_dict)
+            gt = data_dict["gt_st"]
+            if self.dequantize:
+                gt += torch.rand_like(gt) / 100
+            base_pos = self.get_base_pos(data_dict)
+            loss = -self.flow._log_prob_separate_torch(base_pos, gt, dist_args)
+            loss = loss.mean()
+            self.optimizer.zero_grad()
+            loss.backward()
+            self.optimizer.step()
+        self.flow.invalidate()
+        return {"loss": loss.mean().item()}
 
     def get_base_pos(self, data_dict: Dict) -> torch.Tensor:
         """fastpredNF.py:204-213."""
@@ -156,7 +188,8 @@ class fastpredNF_TP(nn.Module):
 
     def save(self, epoch: int = 0, path: Path = None) -> None:
         path = self.output_path / "ckpt.pt" if path is None else path
-        torch.save({"epoch": epoch, "state": self.state_dict(), "optim_state": {}}, path)
+        torch.save({"epoch": epoch, "state": self.state_dict(),
+                    "optim_state": self.optimizer.state_dict() if self.optimizer is not None else {}}, path)
 
     def check_saved_path(self, path: Path = None) -> bool:
         path = self.output_path / "ckpt.pt" if path is None else path
@@ -174,4 +207,8 @@ class fastpredNF_TP(nn.Module):
             raise RuntimeError(f"checkpoint {path} does not match this model: missing/unexpected keys {bad[:8]}"
                                f"{' ...' if len(bad) > 8 else ''} ({len(bad)} in total)")
         self.flow.invalidate()
+        if ckpt.get("optim_state"):      # optimizer state travels with the checkpoint (fastpredNF.py:240-241)
+            if self.optimizer is None:
+                self.build_optimizer()
+            self.optimizer.load_state_dict(ckpt["optim_state"])
         return ckpt["epoch"]

@@ -60,8 +60,13 @@ def test_mirror_state_dict_layout_and_cpu_refusal():
     f.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
     blob = packing.flatten_state(spec, f.state_dict())
     np.testing.assert_array_equal(blob, packing.flatten_state(spec, params))
+    f.eval()                              # inference mode: fused kernels only, and they need a B200
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         f.log_prob(torch.zeros(1, 2), torch.zeros(1, 12, 2), torch.zeros(1, 12, 16))
+    with torch.no_grad():                 # train() mode without grad is still inference
+        f.train()
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            f.log_prob(torch.zeros(1, 2), torch.zeros(1, 12, 2), torch.zeros(1, 12, 16))
     with pytest.raises(ValueError):
         bad = dict(params)
         bad["var"] = np.zeros((3, 2), np.float32)
