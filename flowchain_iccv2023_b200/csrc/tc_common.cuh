@@ -32,13 +32,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a CUDA error (trap), never as a hung GPU box.
+// Bounded wait: a protocol bug must surface as a CUDA error (trap) within seconds, never as a hung GPU box.
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;          // fast path (already complete)
+    const unsigned long long t0 = global_ns();
 #pragma unroll 1                                      // keep every wait site a handful of instructions (I-cache!)
-    for (uint32_t i = 0; i < (1u << 24); ++i)
-        if (mbar_try_wait(bar, parity)) return;
-    __trap();
+    while (!mbar_try_wait(bar, parity))
+        if (global_ns() - t0 > 4000000000ull) __trap();      // 4 s: no legitimate wait in these kernels is longer than milliseconds
 }
 
 // ---- 1-D bulk copy global -> shared (TMA engine, completes on an mbarrier) -----------------------
