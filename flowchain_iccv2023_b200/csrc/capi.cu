@@ -275,6 +275,7 @@ extern "C" int fc_load_weights(fc_handle* h, const float* blob, size_t n_floats,
         std::vector<unsigned char> img2;
         std::vector<fc::T2Step> st2;
         fc::tc2_pack(d, plans, tcsrc, i == 0 ? 3 : 1, img2, st2, h->t2dims[i], h->smem_optin);
+        if (h->t2dims[i].supported && !fc::tc3_fits(st2, h->smem_optin)) h->t2dims[i].supported = 0;    // -> wide kernel
         h->t2steps_host[i] = st2;
         FC_CUDA(h, cudaFree(h->d_t2img[i])); h->d_t2img[i] = nullptr;
         FC_CUDA(h, cudaFree(h->d_t2steps[i])); h->d_t2steps[i] = nullptr;

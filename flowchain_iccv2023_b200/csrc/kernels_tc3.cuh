@@ -295,6 +295,51 @@ __device__ __forceinline__ void t3_producer(const T2Step* __restrict__ steps, co
     T3_ITEM_END
 }
 
+// All MMAs of one job (= net-layer of one tile): D = A_hi W_hi + A_lo W_hi + A_hi W_lo over NK K-steps of 16.
+// TS: A operand in tensor memory (columns ta_hi / ta_lo, 8 columns per K-step); otherwise shared-memory descriptors.
+template <int NPASS, int NK, bool TS>
+__device__ __forceinline__ void issue_job(uint32_t acc, uint32_t ta_hi, uint32_t ta_lo, uint64_t ahi, uint64_t alo, uint64_t dhi, uint64_t dlo,
+                                          uint32_t idesc, uint32_t acc0) {
+#pragma unroll
+    for (int ks = 0; ks < NK; ++ks) {
+        if (TS) umma_ts(acc, ta_hi + ks * 8, dhi + (uint64_t)(ks * 16), idesc, ks > 0 ? 1u : acc0);
+        else umma_bf16(acc, ahi + (uint64_t)(ks * 16), dhi + (uint64_t)(ks * 16), idesc, ks > 0 ? 1u : acc0);
+    }
+    if (NPASS == 3) {
+#pragma unroll
+        for (int ks = 0; ks < NK; ++ks) {
+            if (TS) umma_ts(acc, ta_lo + ks * 8, dhi + (uint64_t)(ks * 16), idesc, 1u);
+            else umma_bf16(acc, alo + (uint64_t)(ks * 16), dhi + (uint64_t)(ks * 16), idesc, 1u);
+        }
+#pragma unroll
+        for (int ks = 0; ks < NK; ++ks) {
+            if (TS) umma_ts(acc, ta_hi + ks * 8, dlo + (uint64_t)(ks * 16), idesc, 1u);
+            else umma_bf16(acc, ahi + (uint64_t)(ks * 16), dlo + (uint64_t)(ks * 16), idesc, 1u);
+        }
+    }
+}
+template <int NPASS, bool TS>
+__device__ __forceinline__ void issue_job_loop(int nk, uint32_t acc, uint32_t ta_hi, uint32_t ta_lo, uint64_t ahi, uint64_t alo, uint64_t dhi,
+                                               uint64_t dlo, uint32_t idesc, uint32_t acc0) {
+#pragma unroll 1
+    for (int ks = 0; ks < nk; ++ks) {
+        if (TS) umma_ts(acc, ta_hi + ks * 8, dhi + (uint64_t)(ks * 16), idesc, ks > 0 ? 1u : acc0);
+        else umma_bf16(acc, ahi + (uint64_t)(ks * 16), dhi + (uint64_t)(ks * 16), idesc, ks > 0 ? 1u : acc0);
+    }
+    if (NPASS == 3) {
+#pragma unroll 1
+        for (int ks = 0; ks < nk; ++ks) {
+            if (TS) umma_ts(acc, ta_lo + ks * 8, dhi + (uint64_t)(ks * 16), idesc, 1u);
+            else umma_bf16(acc, alo + (uint64_t)(ks * 16), dhi + (uint64_t)(ks * 16), idesc, 1u);
+        }
+#pragma unroll 1
+        for (int ks = 0; ks < nk; ++ks) {
+            if (TS) umma_ts(acc, ta_hi + ks * 8, dlo + (uint64_t)(ks * 16), idesc, 1u);
+            else umma_bf16(acc, ahi + (uint64_t)(ks * 16), dlo + (uint64_t)(ks * 16), idesc, 1u);
+        }
+    }
+}
+
 // ===== MMA issuers, one warp per net; every net-layer is issued for tile 0 then tile 1 from the same weight chunk.
 // First layers read their operand from tensor memory (TS), hidden layers from shared memory (SS). =====
 template <int NPASS>
@@ -359,23 +404,23 @@ __device__ __forceinline__ void t3_issuer(const T2Step* __restrict__ steps, cons
                 T3_TR(0x30 + t)          // operand of tile t ready
                 if (leader) {
                     if (fold) umma_bf16(acc, d_ones, d_bias, idesc, 0u);
+                    // straight-line issue for the K widths that occur (16 * nk): with compile-time operand offsets the
+                    // MMAs of a job go out back to back (UTCHMMA after UTCHMMA).  A counted loop costs ~10 set-up
+                    // instructions per MMA in its remainder iterations -- measured ~69 cycles per MMA against the 32 the
+                    // tensor pipe needs at N = 64, i.e. the issue, not the pipe, paced every MMA -> epilogue hand-off.
                     if (src < 2) {
-#pragma unroll 3
-                        for (int ks = 0; ks < nk; ++ks) umma_ts(acc, ta_hi + ks * 8, dhi + (uint64_t)(ks * 16), idesc, ks > 0 ? 1u : acc0);
-                        if (NPASS == 3) {
-#pragma unroll 3
-                            for (int ks = 0; ks < nk; ++ks) umma_ts(acc, ta_lo + ks * 8, dhi + (uint64_t)(ks * 16), idesc, 1u);
-#pragma unroll 3
-                            for (int ks = 0; ks < nk; ++ks) umma_ts(acc, ta_hi + ks * 8, dlo + (uint64_t)(ks * 16), idesc, 1u);
+                        switch (nk) {
+                            case 1: issue_job<NPASS, 1, true>(acc, ta_hi, ta_lo, 0, 0, dhi, dlo, idesc, acc0); break;
+                            case 2: issue_job<NPASS, 2, true>(acc, ta_hi, ta_lo, 0, 0, dhi, dlo, idesc, acc0); break;
+                            case 3: issue_job<NPASS, 3, true>(acc, ta_hi, ta_lo, 0, 0, dhi, dlo, idesc, acc0); break;
+                            default: issue_job_loop<NPASS, true>(nk, acc, ta_hi, ta_lo, 0, 0, dhi, dlo, idesc, acc0); break;
                         }
                     } else {
-#pragma unroll 5
-                        for (int ks = 0; ks < nk; ++ks) umma_bf16(acc, ahi + (uint64_t)(ks * 16), dhi + (uint64_t)(ks * 16), idesc, ks > 0 ? 1u : acc0);
-                        if (NPASS == 3) {
-#pragma unroll 5
-                            for (int ks = 0; ks < nk; ++ks) umma_bf16(acc, alo + (uint64_t)(ks * 16), dhi + (uint64_t)(ks * 16), idesc, 1u);
-#pragma unroll 5
-                            for (int ks = 0; ks < nk; ++ks) umma_bf16(acc, ahi + (uint64_t)(ks * 16), dlo + (uint64_t)(ks * 16), idesc, 1u);
+                        switch (nk) {
+                            case 3: issue_job<NPASS, 3, false>(acc, 0, 0, ahi, alo, dhi, dlo, idesc, acc0); break;
+                            case 4: issue_job<NPASS, 4, false>(acc, 0, 0, ahi, alo, dhi, dlo, idesc, acc0); break;
+                            case 5: issue_job<NPASS, 5, false>(acc, 0, 0, ahi, alo, dhi, dlo, idesc, acc0); break;
+                            default: issue_job_loop<NPASS, false>(nk, acc, 0, 0, ahi, alo, dhi, dlo, idesc, acc0); break;
                         }
                     }
                     umma_commit(&bars->mma_done[t][net]);
@@ -748,6 +793,26 @@ k_separate_tc3(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
     tc_fence_before();
     __syncthreads();
     if (warp == 16) tmem_dealloc(tmem_base, 512);
+}
+
+// Shared-memory feasibility of the two-tile kernel for a packed model (same arithmetic as the launchers below): every
+// step's operand tiles + at least a 2-slot ring of its largest weight chunk must fit, for the per-step launches (width
+// classes) and for the chain / sampler launches (one class for the whole model).  capi.cu routes the model to the wide
+// kernel when this says no (e.g. hidden_size 80: two 26.3 KB slots + 160 KB of operand tiles exceed 227 KB by 512 B).
+inline bool tc3_fits(const std::vector<T2Step>& hsteps, int smem_optin) {
+    int wmax = 64, slot_max = 0;
+    for (const T2Step& st : hsteps) {
+        const int w = st.Wd > st.Hc ? st.Wd : st.Hc;
+        if (w > 80) return false;
+        const int wc = w <= 64 ? 64 : 80;
+        int slot = 0;
+        for (int ci = 0; ci < st.nchunks; ++ci) slot = st.chunk_bytes[ci] > slot ? st.chunk_bytes[ci] : slot;
+        slot = (slot + 127) / 128 * 128;
+        if ((size_t)kT3Header + (size_t)8 * 128 * wc * 2 + (size_t)2 * slot > (size_t)smem_optin) return false;
+        wmax = wc > wmax ? wc : wmax;
+        slot_max = slot > slot_max ? slot : slot_max;
+    }
+    return (size_t)kT3Header + (size_t)8 * 128 * wmax * 2 + (size_t)2 * slot_max <= (size_t)smem_optin;
 }
 
 // Launches the steps in groups of equal operand-width class (hidden width <= 64: 128 KB of operand tiles + a 4-slot weight

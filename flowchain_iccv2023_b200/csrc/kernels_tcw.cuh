@@ -311,25 +311,27 @@ __device__ __forceinline__ void tw_issuer(const TwStep* __restrict__ steps, cons
                 const uint32_t b_hi = smem_u32(m.slots + (size_t)slot * dm.slot_bytes), sboB = (uint32_t)(ksl >> 3) * 128u;
                 const uint64_t dhi = umma_desc(b_hi, 128, sboB), dlo = umma_desc(b_hi + (uint32_t)(N * ksl * 2), 128, sboB);
                 if (leader) {
+                    // straight-line issue (compile-time operand offsets inside the slab), see t3::issue_job
+                    const uint32_t tah = ta_hi + (uint32_t)(kg0 * 8), tal = ta_lo + (uint32_t)(kg0 * 8);
+                    const uint64_t sah = ahi + (uint64_t)(kg0 * 16), sal = alo + (uint64_t)(kg0 * 16);
                     if (src < 2) {
-#pragma unroll 2
-                        for (int kk = 0; kk < nk; ++kk) { umma_ts(acc, ta_hi + (uint32_t)((kg0 + kk) * 8), dhi + (uint64_t)(kk * 16), idesc, accum); accum = 1u; }
-                        if (NPASS == 3) {
-#pragma unroll 2
-                            for (int kk = 0; kk < nk; ++kk) umma_ts(acc, ta_lo + (uint32_t)((kg0 + kk) * 8), dhi + (uint64_t)(kk * 16), idesc, 1u);
-#pragma unroll 2
-                            for (int kk = 0; kk < nk; ++kk) umma_ts(acc, ta_hi + (uint32_t)((kg0 + kk) * 8), dlo + (uint64_t)(kk * 16), idesc, 1u);
+                        switch (nk) {
+                            case 1: t3::issue_job<NPASS, 1, true>(acc, tah, tal, 0, 0, dhi, dlo, idesc, accum); break;
+                            case 2: t3::issue_job<NPASS, 2, true>(acc, tah, tal, 0, 0, dhi, dlo, idesc, accum); break;
+                            case 3: t3::issue_job<NPASS, 3, true>(acc, tah, tal, 0, 0, dhi, dlo, idesc, accum); break;
+                            case 4: t3::issue_job<NPASS, 4, true>(acc, tah, tal, 0, 0, dhi, dlo, idesc, accum); break;
+                            default: t3::issue_job_loop<NPASS, true>(nk, acc, tah, tal, 0, 0, dhi, dlo, idesc, accum); break;
                         }
                     } else {
-#pragma unroll 2
-                        for (int kk = 0; kk < nk; ++kk) { umma_bf16(acc, ahi + (uint64_t)((kg0 + kk) * 16), dhi + (uint64_t)(kk * 16), idesc, accum); accum = 1u; }
-                        if (NPASS == 3) {
-#pragma unroll 2
-                            for (int kk = 0; kk < nk; ++kk) umma_bf16(acc, alo + (uint64_t)((kg0 + kk) * 16), dhi + (uint64_t)(kk * 16), idesc, 1u);
-#pragma unroll 2
-                            for (int kk = 0; kk < nk; ++kk) umma_bf16(acc, ahi + (uint64_t)((kg0 + kk) * 16), dlo + (uint64_t)(kk * 16), idesc, 1u);
+                        switch (nk) {
+                            case 1: t3::issue_job<NPASS, 1, false>(acc, 0, 0, sah, sal, dhi, dlo, idesc, accum); break;
+                            case 2: t3::issue_job<NPASS, 2, false>(acc, 0, 0, sah, sal, dhi, dlo, idesc, accum); break;
+                            case 3: t3::issue_job<NPASS, 3, false>(acc, 0, 0, sah, sal, dhi, dlo, idesc, accum); break;
+                            case 4: t3::issue_job<NPASS, 4, false>(acc, 0, 0, sah, sal, dhi, dlo, idesc, accum); break;
+                            default: t3::issue_job_loop<NPASS, false>(nk, acc, 0, 0, sah, sal, dhi, dlo, idesc, accum); break;
                         }
                     }
+                    accum = 1u;
                     umma_commit(&bars->empty[slot]);          // slab consumed -> slot back to the producer
                 }
                 __syncwarp();

@@ -33,18 +33,23 @@ __global__ void __launch_bounds__(640, 1) k_mb(int N, int ts_mode, int n_stream,
     if (tid == 0) stop = 0;
     __syncthreads();
     if (warp == 0) {
-        if ((tid & 31) == 0) {
+        uint32_t leader;
+        asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(leader));
+        if (leader) {      // same issue pattern as the fused kernels: warp-uniform operands, one elected lane
             const uint32_t idesc = umma_idesc_f16(128, N);
             const uint64_t da = umma_desc(smem_u32(sA), 128, 8 * 128), db = umma_desc(smem_u32(sB), 128, 8 * 128);
             const uint32_t ta = tm + 384;      // A operand columns (garbage is fine)
             uint32_t phase = 0;
-            // (a) throughput
+            // (a) throughput: straight-line groups of 16 MMAs with compile-time descriptor offsets (no per-MMA set-up)
             long long t0 = clock64();
             for (int r = 0; r < reps; ++r) {
-                for (int i = 0; i < n_stream; ++i) {
-                    const int ks = i & 3;
-                    if (ts_mode) umma_ts(tm, ta + ks * 8, db + (uint64_t)(ks * 16), idesc, 1u);
-                    else umma_bf16(tm, da + (uint64_t)(ks * 16), db + (uint64_t)(ks * 16), idesc, 1u);
+                for (int i = 0; i < n_stream; i += 16) {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const int ks = q & 3;
+                        if (ts_mode) umma_ts(tm, ta + ks * 8, db + (uint64_t)(ks * 16), idesc, 1u);
+                        else umma_bf16(tm, da + (uint64_t)(ks * 16), db + (uint64_t)(ks * 16), idesc, 1u);
+                    }
                 }
                 umma_commit(bar);
                 mbar_wait(bar, phase); phase ^= 1u;
@@ -55,10 +60,19 @@ __global__ void __launch_bounds__(640, 1) k_mb(int N, int ts_mode, int n_stream,
             long long acc_issue = 0, acc_done = 0;
             for (int r = 0; r < reps; ++r) {
                 long long a0 = clock64();
-                for (int i = 0; i < n_job; ++i) {
-                    const int ks = i & 3;
-                    if (ts_mode) umma_ts(tm, ta + ks * 8, db + (uint64_t)(ks * 16), idesc, i > 0 ? 1u : 0u);
-                    else umma_bf16(tm, da + (uint64_t)(ks * 16), db + (uint64_t)(ks * 16), idesc, i > 0 ? 1u : 0u);
+                if (n_job == 13) {
+#pragma unroll
+                    for (int i = 0; i < 13; ++i) {
+                        const int ks = i & 3;
+                        if (ts_mode) umma_ts(tm, ta + ks * 8, db + (uint64_t)(ks * 16), idesc, i > 0 ? 1u : 0u);
+                        else umma_bf16(tm, da + (uint64_t)(ks * 16), db + (uint64_t)(ks * 16), idesc, i > 0 ? 1u : 0u);
+                    }
+                } else {
+                    for (int i = 0; i < n_job; ++i) {
+                        const int ks = i & 3;
+                        if (ts_mode) umma_ts(tm, ta + ks * 8, db + (uint64_t)(ks * 16), idesc, i > 0 ? 1u : 0u);
+                        else umma_bf16(tm, da + (uint64_t)(ks * 16), db + (uint64_t)(ks * 16), idesc, i > 0 ? 1u : 0u);
+                    }
                 }
                 umma_commit(bar);
                 long long a1 = clock64();
