@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FLOWCHAIN_B200_LIB", os.path.join(_HERE, "libflowchain_b200.so"))
@@ -23,6 +23,7 @@ SYMBOLS = [
     "fc_create", "fc_destroy", "fc_last_error", "fc_weight_blob_floats", "fc_load_weights",
     "fc_weights_version", "fc_log_prob", "fc_log_prob_sequential", "fc_grid_log_prob", "fc_grid_log_prob_multicast",
     "fc_sample_with_log_prob", "fc_base_normalizer", "fc_update", "fc_update_lazy", "fc_launch_count", "fc_tc_gemm_selftest",
+    "fc_grid_density_maps", "fc_to_trajectories", "fc_best_of_n",
 ]
 
 
@@ -76,6 +77,13 @@ def load():
     lib.fc_update.restype = c_int
     lib.fc_update_lazy.argtypes = [c_void_p, fp, c_int, fp, fp, fp, c_int64, c_int64, c_void_p]
     lib.fc_update_lazy.restype = c_int
+    lib.fc_grid_density_maps.argtypes = [c_void_p, fp, fp, fp, fp, fp, fp, fp, fp, c_uint64, c_int, fp,
+                                         c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p]
+    lib.fc_grid_density_maps.restype = c_int
+    lib.fc_to_trajectories.argtypes = [c_void_p, fp, fp, fp, c_float, c_float, c_int, fp, c_int64, c_int64, c_int, c_int, c_void_p]
+    lib.fc_to_trajectories.restype = c_int
+    lib.fc_best_of_n.argtypes = [c_void_p, fp, fp, fp, fp, fp, c_float, c_float, c_int, fp, fp, fp, fp, c_int64, c_int64, c_int, c_void_p]
+    lib.fc_best_of_n.restype = c_int
     lib.fc_tc_gemm_selftest.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int]
     lib.fc_tc_gemm_selftest.restype = c_int
     lib.fc_launch_count.argtypes = [c_void_p]

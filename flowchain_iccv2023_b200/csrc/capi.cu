@@ -12,6 +12,7 @@
 
 #include "../../include/flowchain_b200.h"
 #include "kernels_fp32.cuh"
+#include "kernels_post.cuh"
 #include "kernels_tc3.cuh"
 #include "kernels_tcw.cuh"
 #include "plan.h"
@@ -443,10 +444,20 @@ extern "C" int fc_log_prob_sequential(fc_handle* h, const float* base_pos, const
     return launch_density(h, a, MODE_SEQUENTIAL, precision, (cudaStream_t)stream);
 }
 
+namespace {
+struct QueryMap {          // affine query transform + output epilogue of the position-space maps (RowArgs::qscale ...)
+    const float* origin = nullptr;      // (A, T, 2)
+    const float* inv_scale = nullptr;   // (A, 2)
+    const float* log_jac = nullptr;     // (A)
+    int as_prob = 0;
+};
+}  // namespace
+
 static int grid_log_prob_impl(fc_handle* h, const float* base_pos, const float* cond, const float* cond_traj,
                               const float* grid, const float* eps, uint64_t seed, int prefix_mode, int sequential,
                               int K, float* out, int64_t out_agent_stride, int64_t out_point_stride,
-                              int64_t out_step_stride, int64_t A, int64_t G, int precision, void* stream_, int multicast) {
+                              int64_t out_step_stride, int64_t A, int64_t G, int precision, void* stream_, int multicast,
+                              const QueryMap* qm = nullptr) {
     FC_ENTER(h);
     cudaStream_t stream = (cudaStream_t)stream_;
     if (A < 0 || G < 0) return fail(h, "negative size");
@@ -465,6 +476,10 @@ static int grid_log_prob_impl(fc_handle* h, const float* base_pos, const float* 
     a.N = A * G * K; a.PPA = G * K; a.K = K;
     a.seq_klo = 0; a.seq_jlo = 0;
     a.out_sys = multicast ? 1 : 0;
+    if (qm != nullptr) {
+        a.qshift = qm->origin; a.qshift_sa = 2LL * T; a.qshift_st = 2;
+        a.qscale = qm->inv_scale; a.out_shift = qm->log_jac; a.out_exp = qm->as_prob;
+    }
     // K = 2^j <= 32: the K samples of a point are consecutive rows = consecutive lanes, and logsumexp_k - log K is reduced
     // with warp shuffles inside the density kernel (one store per point and step); other K go through a scratch buffer
     const bool fuse_k = K > 1 && K <= 32 && (K & (K - 1)) == 0;
@@ -609,6 +624,57 @@ extern "C" int fc_update(fc_handle* h, const float* new_pos, int t, const float*
 extern "C" int fc_update_lazy(fc_handle* h, const float* new_pos, int t, const float* prob_st_0, const float* normalizer,
                               float* base_lp_t, int64_t A, int64_t S, void* stream) {
     return update_impl(h, new_pos, t, prob_st_0, nullptr, normalizer, base_lp_t, A, S, stream, true);
+}
+
+extern "C" int fc_grid_density_maps(fc_handle* h, const float* base_pos, const float* cond, const float* cond_traj,
+                                    const float* grid_xy, const float* origin, const float* inv_scale, const float* log_jac,
+                                    const float* eps, uint64_t seed, int as_prob, float* out, int64_t out_agent_stride,
+                                    int64_t out_point_stride, int64_t out_step_stride, int64_t A, int64_t G, int precision,
+                                    void* stream) {
+    if (!h) return fail(nullptr, "null handle");
+    if (!cond_traj || !origin || !inv_scale) return fail(h, "fc_grid_density_maps needs cond_traj, origin and inv_scale");
+    QueryMap qm;
+    qm.origin = origin; qm.inv_scale = inv_scale; qm.log_jac = log_jac; qm.as_prob = as_prob ? 1 : 0;
+    return grid_log_prob_impl(h, base_pos, cond, cond_traj, grid_xy, eps, seed, FC_PREFIX_SHARED, 0, 1, out, out_agent_stride,
+                              out_point_stride, out_step_stride, A, G, precision, stream, 0, &qm);
+}
+
+extern "C" int fc_to_trajectories(fc_handle* h, const float* state_st, const float* offset, const float* dt, float std0, float std1,
+                                  int state_mode, float* out, int64_t A, int64_t S, int Tk, int ncol, void* stream) {
+    FC_ENTER(h);
+    if (A < 0 || S < 0 || Tk < 0) return fail(h, "negative size");
+    if (ncol != 2 && ncol != 3) return fail(h, "ncol must be 2 (positions) or 3 (positions + log p), got %d", ncol);
+    if (state_mode != 0 && state_mode != 1) return fail(h, "state_mode must be 0 (state_p) or 1 (state_v); 'state_a' is asserted out in the reference too");
+    if (A == 0 || S == 0 || Tk == 0) return 0;
+    if (!state_st || !offset || !out) return fail(h, "null tensor pointer");
+    const long long rows = (long long)A * S;
+    const int per = Tk * ncol;
+    const size_t smem = (size_t)kTrajRows * (per | 1) * sizeof(float);
+    if (smem > 48 * 1024) FC_CUDA(h, cudaFuncSetAttribute(k_to_trajectories, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if ((int)smem > h->smem_optin) return fail(h, "rows too long for fc_to_trajectories (%d floats)", per);
+    const long long blocks = (rows + kTrajRows - 1) / kTrajRows;
+    if (blocks > 0x7fffffffLL) return fail(h, "too many rows");
+    k_to_trajectories<<<(unsigned)blocks, kTrajRows, smem, (cudaStream_t)stream>>>(state_st, offset, dt, std0, std1, state_mode, out, rows, S, Tk, ncol);
+    h->launches++;
+    FC_CUDA(h, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int fc_best_of_n(fc_handle* h, const float* cand_st, const float* gt, const float* last_obs, const float* dt,
+                            const float* fallback_st, float std0, float std1, int state_mode, float* ade_min, float* fde_min,
+                            int32_t* ade_arg, int32_t* fde_arg, int64_t A, int64_t N, int T, void* stream) {
+    FC_ENTER(h);
+    if (A < 0 || N < 0 || T < 1) return fail(h, "bad size");
+    if (state_mode != 0 && state_mode != 1) return fail(h, "state_mode must be 0 (state_p) or 1 (state_v)");
+    if (A == 0) return 0;
+    if (N == 0) return fail(h, "no candidates");
+    if (!cand_st || !gt || !last_obs || !ade_min || !fde_min) return fail(h, "null tensor pointer");
+    const long long blocks = (A + 3) / 4;
+    k_best_of_n<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(cand_st, gt, last_obs, dt, fallback_st, std0, std1, state_mode, ade_min,
+                                                                   fde_min, ade_arg, fde_arg, A, N, T);
+    h->launches++;
+    FC_CUDA(h, cudaGetLastError());
+    return 0;
 }
 
 extern "C" int fc_tc_gemm_selftest(const float* A, const float* B, float* D, int N, int K, int device, int mode) {

@@ -446,8 +446,9 @@ k_separate_fp32(const StepPlan* __restrict__ plans, const float* __restrict__ wb
     __syncthreads();
     const int r = threadIdx.x;
     if (r < R) {
-        const float* xp = src_at(a.x, t.ROWA[r], t.ROWP[r], step);
-        t.Z[r] = __ldg(xp); t.Z[R + r] = __ldg(xp + 1);
+        float q0, q1;
+        load_query(a, t.ROWA[r], t.ROWP[r], step, q0, q1);
+        t.Z[r] = q0; t.Z[R + r] = q1;
         const float* pp = step == 0 ? src_at(a.base, t.ROWA[r], t.ROWP[r], 0)
                                     : src_at(a.prefix, t.ROWA[r], t.ROWP[r], step - 1);
         t.PREV[r] = __ldg(pp); t.PREV[R + r] = __ldg(pp + 1);

@@ -13,12 +13,28 @@
 #include "kernels_fp32.cuh"
 #include "tc_f16x3.cuh"
 
+// FC_T3_SPLIT_NETS = 1: inside a tile, column part p (4 warps) runs the hidden-layer epilogues of NET p only, over all
+// columns of its rows -- the s-net (tanh, XU-bound) and t-net (ReLU) chains of a tile advance on different warps instead
+// of taking turns on the same eight.  0: the round-1 schedule (both parts share every epilogue, nets in turn).
+#ifndef FC_T3_SPLIT_NETS
+#define FC_T3_SPLIT_NETS 1
+#endif
+
 namespace fc {
 
-// tensor-memory column map of one tile (256 columns per tile)
-constexpr uint32_t kT3Acc0 = 0, kT3Acc1 = 80;            // fp32 accumulators of net 0 / 1 (N <= 80)
+// tensor-memory column map of one tile (256 columns per tile), two layouts:
+//  HTS = false (layers up to 80 wide, chain mode, sampler): accumulators + the narrow FIRST-layer operands in tensor
+//        memory (TS-mode MMAs), hidden-layer operands in shared memory (SS-mode MMAs);
+//  HTS = true  (per-step launches whose layers are all <= 64 wide): accumulators + the HIDDEN-layer operands (hi, lo of
+//        both nets, K <= 64) in tensor memory, first-layer operands (K <= 32) in shared memory.  An SS-mode MMA pays
+//        ~44 cycles for reading its [128 x 16] A tile from shared memory on top of the N/2 cycles of math (measured,
+//        tools/mb_mma.cu: N = 64: 76 cycles SS vs 43 TS); the hidden layers are 80 % of the MMAs, so they get the TS slot.
+constexpr uint32_t kT3Acc0 = 0, kT3Acc1 = 80;            // HTS = false: fp32 accumulators of net 0 / 1 (N <= 80)
 constexpr uint32_t kT3InHi = 160, kT3InLo = 184;         // [z|w, cond, prefix] operand, K <= 48
 constexpr uint32_t kT3UHi = 208, kT3ULo = 232;           // [u, mx] operand, K <= 48
+constexpr uint32_t kT3HAcc1 = 64;                        // HTS = true: accumulators [0, 64), [64, 128)
+constexpr uint32_t kT3H0Hi = 128, kT3H0Lo = 160, kT3H1Hi = 192, kT3H1Lo = 224;   // hidden operands of net 0 / 1, K <= 64
+constexpr int kT3InuK = 32;                              // HTS = true: widest first-layer operand, [128 x 32] fp16 tiles in smem
 constexpr uint32_t kT3TileCols = 256;
 constexpr int kT3Threads = 16 * 32 + 128;                 // 2 x 8 compute warps + a service warpgroup (producer, 2 issuers, 1 idle)
 constexpr int kT3ComputeRegs = 104, kT3ServiceRegs = 56;   // setmaxnreg split of the register file (see the kernel)
@@ -73,7 +89,7 @@ __device__ __forceinline__ void sts128(uint32_t saddr, const uint32_t* v) {
 }
 
 // 8 activated values -> hi / lo fp16 rows of the next layer's shared-memory operand tile
-template <int NPASS, int ACT, bool DOT, bool WRITE, bool BIAS>
+template <int NPASS, int ACT, bool DOT, bool WRITE, bool BIAS, bool HTS = false>
 __device__ __forceinline__ void epi_chunk3(float* u, int c0, const float4 b0, const float4 b1, uint32_t wlast, uint32_t ohi, uint32_t olo, uint32_t koff, float& dot) {
     if (BIAS) { u[0] += b0.x; u[1] += b0.y; u[2] += b0.z; u[3] += b0.w; u[4] += b1.x; u[5] += b1.y; u[6] += b1.z; u[7] += b1.w; }
     if (ACT == ACT_T) {
@@ -94,21 +110,28 @@ __device__ __forceinline__ void epi_chunk3(float* u, int c0, const float4 b0, co
     if (WRITE) {
         uint32_t hi[4], lo[4];
         split8<NPASS, ACT == ACT_R>(u, hi, lo);
-        // canonical K-major tile: 8 consecutive K elements of one row = one 16-byte store
-        const uint32_t off = koff + (uint32_t)(c0 >> 3) * 128u;
-        sts128(ohi + off, hi);
-        if (NPASS == 3) sts128(olo + off, lo);
+        if (HTS) {      // next layer's A operand in tensor memory: 8 fp16 = 4 packed columns of this thread's lane
+            tmem_st4(ohi + (uint32_t)(c0 >> 1), hi);
+            if (NPASS == 3) tmem_st4(olo + (uint32_t)(c0 >> 1), lo);
+        } else {        // canonical K-major tile in shared memory: 8 consecutive K elements of one row = one 16-byte store
+            const uint32_t off = koff + (uint32_t)(c0 >> 3) * 128u;
+            sts128(ohi + off, hi);
+            if (NPASS == 3) sts128(olo + off, lo);
+        }
     }
 }
 
 // koff = (row/8) * (W/8) * 128 + (row%8) * 16 : byte offset of this thread's row inside a [128 x W] canonical tile
 // BIAS = false: the bias is already inside the accumulator (folded chunk, see the issuer)
-template <int NPASS, int ACT, bool DOT, bool WRITE, bool BIAS>
+// ALLCOLS: the thread owns every 8-column chunk of its row (one net per column part, see FC_T3_SPLIT_NETS) instead of
+// every other one
+template <int NPASS, int ACT, bool DOT, bool WRITE, bool BIAS, bool HTS = false, bool ALLCOLS = false>
 __device__ __noinline__ float epi_hidden3(uint32_t acc, uint32_t ohi, uint32_t olo, uint32_t bias, uint32_t wlast, int part, int W, uint32_t koff) {
+    constexpr int CSTEP = ALLCOLS ? 8 : 16;
     float dot = 0.0f;
 #pragma unroll 1
-    for (int c0 = part * 8; c0 < W; c0 += 32) {
-        const int c1 = c0 + 16;
+    for (int c0 = part * 8; c0 < W; c0 += 2 * CSTEP) {
+        const int c1 = c0 + CSTEP;
         float v0[8], v1[8];
         tmem_ld8(acc + (uint32_t)c0, v0);
         if (c1 < W) tmem_ld8(acc + (uint32_t)c1, v1);
@@ -119,8 +142,8 @@ __device__ __noinline__ float epi_hidden3(uint32_t acc, uint32_t ohi, uint32_t o
             b10 = lds128(bias + (uint32_t)c1 * 4); b11 = lds128(bias + (uint32_t)c1 * 4 + 16);
         }
         tmem_wait_ld();
-        epi_chunk3<NPASS, ACT, DOT, WRITE, BIAS>(v0, c0, b00, b01, wlast, ohi, olo, koff, dot);
-        if (c1 < W) epi_chunk3<NPASS, ACT, DOT, WRITE, BIAS>(v1, c1, b10, b11, wlast, ohi, olo, koff, dot);
+        epi_chunk3<NPASS, ACT, DOT, WRITE, BIAS, HTS>(v0, c0, b00, b01, wlast, ohi, olo, koff, dot);
+        if (c1 < W) epi_chunk3<NPASS, ACT, DOT, WRITE, BIAS, HTS>(v1, c1, b10, b11, wlast, ohi, olo, koff, dot);
     }
     return dot;
 }
@@ -128,13 +151,14 @@ __device__ __noinline__ float epi_hidden3(uint32_t acc, uint32_t ohi, uint32_t o
 // Epilogue of a layer that is exactly 16 * NB columns wide: this thread's NB chunks are processed in unguarded pairs,
 // so the compiler interleaves the 16 independent value chains of a pair (the guarded loop above keeps every chunk in
 // its own basic block); all NB at once measured slower than pairs.
-template <int NPASS, int ACT, bool DOT, bool WRITE, bool BIAS, int NB>
+template <int NPASS, int ACT, bool DOT, bool WRITE, bool BIAS, int NB, bool HTS = false, bool ALLCOLS = false>
 __device__ __noinline__ float epi_hidden3_nb(uint32_t acc, uint32_t ohi, uint32_t olo, uint32_t bias, uint32_t wlast, int part, uint32_t koff) {
+    constexpr int CSTEP = ALLCOLS ? 8 : 16;
     float dot = 0.0f;
     const int c0 = part * 8;
 #pragma unroll
     for (int j = 0; j < NB; j += 2) {
-        const int ca = c0 + 16 * j, cb = ca + 16;
+        const int ca = c0 + CSTEP * j, cb = ca + CSTEP;
         float v0[8], v1[8];
         tmem_ld8(acc + (uint32_t)ca, v0);
         if (j + 1 < NB) tmem_ld8(acc + (uint32_t)cb, v1);
@@ -144,17 +168,29 @@ __device__ __noinline__ float epi_hidden3_nb(uint32_t acc, uint32_t ohi, uint32_
             if (j + 1 < NB) { b10 = lds128(bias + (uint32_t)cb * 4); b11 = lds128(bias + (uint32_t)cb * 4 + 16); }
         }
         tmem_wait_ld();
-        epi_chunk3<NPASS, ACT, DOT, WRITE, BIAS>(v0, ca, b00, b01, wlast, ohi, olo, koff, dot);
-        if (j + 1 < NB) epi_chunk3<NPASS, ACT, DOT, WRITE, BIAS>(v1, cb, b10, b11, wlast, ohi, olo, koff, dot);
+        epi_chunk3<NPASS, ACT, DOT, WRITE, BIAS, HTS>(v0, ca, b00, b01, wlast, ohi, olo, koff, dot);
+        if (j + 1 < NB) epi_chunk3<NPASS, ACT, DOT, WRITE, BIAS, HTS>(v1, cb, b10, b11, wlast, ohi, olo, koff, dot);
     }
     return dot;
 }
-template <int NPASS, int ACT, bool DOT, bool WRITE, bool BIAS>
+template <int NPASS, int ACT, bool DOT, bool WRITE, bool BIAS, bool HTS = false>
 __device__ __forceinline__ float epi_layer3(uint32_t acc, uint32_t ohi, uint32_t olo, uint32_t bias, uint32_t wlast, int part, int W, uint32_t koff) {
-    if (W == 64) return epi_hidden3_nb<NPASS, ACT, DOT, WRITE, BIAS, 4>(acc, ohi, olo, bias, wlast, part, koff);
-    if (W == 48) return epi_hidden3_nb<NPASS, ACT, DOT, WRITE, BIAS, 3>(acc, ohi, olo, bias, wlast, part, koff);
-    if (W == 80) return epi_hidden3_nb<NPASS, ACT, DOT, WRITE, BIAS, 5>(acc, ohi, olo, bias, wlast, part, koff);
-    return epi_hidden3<NPASS, ACT, DOT, WRITE, BIAS>(acc, ohi, olo, bias, wlast, part, W, koff);
+#if FC_T3_SPLIT_NETS
+    // one net per column part: the thread walks all W columns of its row (`part` only selected the net)
+    if (W == 64) return epi_hidden3_nb<NPASS, ACT, DOT, WRITE, BIAS, 8, HTS, true>(acc, ohi, olo, bias, wlast, 0, koff);
+    if (W == 48) return epi_hidden3_nb<NPASS, ACT, DOT, WRITE, BIAS, 6, HTS, true>(acc, ohi, olo, bias, wlast, 0, koff);
+    if (!HTS && W == 80) return epi_hidden3_nb<NPASS, ACT, DOT, WRITE, BIAS, 10, HTS, true>(acc, ohi, olo, bias, wlast, 0, koff);
+    return epi_hidden3<NPASS, ACT, DOT, WRITE, BIAS, HTS, true>(acc, ohi, olo, bias, wlast, 0, W, koff);
+#else
+    if (W == 64) return epi_hidden3_nb<NPASS, ACT, DOT, WRITE, BIAS, 4, HTS>(acc, ohi, olo, bias, wlast, part, koff);
+    if (W == 48) return epi_hidden3_nb<NPASS, ACT, DOT, WRITE, BIAS, 3, HTS>(acc, ohi, olo, bias, wlast, part, koff);
+    if (!HTS && W == 80) return epi_hidden3_nb<NPASS, ACT, DOT, WRITE, BIAS, 5, HTS>(acc, ohi, olo, bias, wlast, part, koff);
+    return epi_hidden3<NPASS, ACT, DOT, WRITE, BIAS, HTS>(acc, ohi, olo, bias, wlast, part, W, koff);
+#endif
+}
+__device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
+__device__ __forceinline__ void lds128u(uint32_t saddr, uint32_t* v) {
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(saddr));
 }
 
 // per-thread view of its group (tile)
@@ -342,7 +378,20 @@ __device__ __forceinline__ void issue_job_loop(int nk, uint32_t acc, uint32_t ta
 
 // ===== MMA issuers, one warp per net; every net-layer is issued for tile 0 then tile 1 from the same weight chunk.
 // First layers read their operand from tensor memory (TS), hidden layers from shared memory (SS). =====
-template <int NPASS>
+template <int NPASS, bool TS>
+__device__ __forceinline__ void issue_dispatch(int nk, uint32_t acc, uint32_t ta_hi, uint32_t ta_lo, uint64_t ahi, uint64_t alo, uint64_t dhi,
+                                               uint64_t dlo, uint32_t idesc, uint32_t acc0) {
+    switch (nk) {
+        case 1: issue_job<NPASS, 1, TS>(acc, ta_hi, ta_lo, ahi, alo, dhi, dlo, idesc, acc0); break;
+        case 2: issue_job<NPASS, 2, TS>(acc, ta_hi, ta_lo, ahi, alo, dhi, dlo, idesc, acc0); break;
+        case 3: issue_job<NPASS, 3, TS>(acc, ta_hi, ta_lo, ahi, alo, dhi, dlo, idesc, acc0); break;
+        case 4: issue_job<NPASS, 4, TS>(acc, ta_hi, ta_lo, ahi, alo, dhi, dlo, idesc, acc0); break;
+        case 5: issue_job<NPASS, 5, TS>(acc, ta_hi, ta_lo, ahi, alo, dhi, dlo, idesc, acc0); break;
+        default: issue_job_loop<NPASS, TS>(nk, acc, ta_hi, ta_lo, ahi, alo, dhi, dlo, idesc, acc0); break;
+    }
+}
+
+template <int NPASS, bool HTS>
 __device__ __forceinline__ void t3_issuer(const T2Step* __restrict__ steps, const T3Dims& dm, long long pairs_per_step, long long total_items,
                                        uint8_t* smem, uint32_t tmem_base, int net) {
     const T3Smem m = t3_smem(smem, dm);
@@ -388,9 +437,12 @@ __device__ __forceinline__ void t3_issuer(const T2Step* __restrict__ steps, cons
 #pragma unroll 1
             for (int t = 0; t < ntile; ++t) {
                 const uint32_t tb0 = tmem_base + (uint32_t)t * kT3TileCols;
-                const uint32_t acc = tb0 + (net ? kT3Acc1 : kT3Acc0);
-                const uint32_t ta_hi = tb0 + (src == 0 ? kT3InHi : kT3UHi), ta_lo = tb0 + (src == 0 ? kT3InLo : kT3ULo);
-                const uint32_t sa = smem_u32(hbuf) + (uint32_t)(t * 4 + net * 2) * h_stride;
+                // operand of the job: tensor memory (TS) or shared memory (SS), by layout (see the column map)
+                const uint32_t acc = tb0 + (net ? (HTS ? kT3HAcc1 : kT3Acc1) : kT3Acc0);
+                const bool ts_job = HTS ? src == 2 : src < 2;
+                const uint32_t ta_hi = tb0 + (HTS ? (net ? kT3H1Hi : kT3H0Hi) : (src == 0 ? kT3InHi : kT3UHi));
+                const uint32_t ta_lo = tb0 + (HTS ? (net ? kT3H1Lo : kT3H0Lo) : (src == 0 ? kT3InLo : kT3ULo));
+                const uint32_t sa = smem_u32(hbuf) + (uint32_t)(t * 4 + (HTS ? src : net) * 2) * h_stride;
                 const uint64_t ahi = umma_desc(sa, 128, sbo), alo = umma_desc(sa + h_stride, 128, sbo);
                 // ---- critical path: operand of this tile ready -> MMAs -> commit ----
                 if (w == 3) {
@@ -408,21 +460,8 @@ __device__ __forceinline__ void t3_issuer(const T2Step* __restrict__ steps, cons
                     // MMAs of a job go out back to back (UTCHMMA after UTCHMMA).  A counted loop costs ~10 set-up
                     // instructions per MMA in its remainder iterations -- measured ~69 cycles per MMA against the 32 the
                     // tensor pipe needs at N = 64, i.e. the issue, not the pipe, paced every MMA -> epilogue hand-off.
-                    if (src < 2) {
-                        switch (nk) {
-                            case 1: issue_job<NPASS, 1, true>(acc, ta_hi, ta_lo, 0, 0, dhi, dlo, idesc, acc0); break;
-                            case 2: issue_job<NPASS, 2, true>(acc, ta_hi, ta_lo, 0, 0, dhi, dlo, idesc, acc0); break;
-                            case 3: issue_job<NPASS, 3, true>(acc, ta_hi, ta_lo, 0, 0, dhi, dlo, idesc, acc0); break;
-                            default: issue_job_loop<NPASS, true>(nk, acc, ta_hi, ta_lo, 0, 0, dhi, dlo, idesc, acc0); break;
-                        }
-                    } else {
-                        switch (nk) {
-                            case 3: issue_job<NPASS, 3, false>(acc, 0, 0, ahi, alo, dhi, dlo, idesc, acc0); break;
-                            case 4: issue_job<NPASS, 4, false>(acc, 0, 0, ahi, alo, dhi, dlo, idesc, acc0); break;
-                            case 5: issue_job<NPASS, 5, false>(acc, 0, 0, ahi, alo, dhi, dlo, idesc, acc0); break;
-                            default: issue_job_loop<NPASS, false>(nk, acc, 0, 0, ahi, alo, dhi, dlo, idesc, acc0); break;
-                        }
-                    }
+                    if (ts_job) issue_dispatch<NPASS, true>(nk, acc, ta_hi, ta_lo, 0, 0, dhi, dlo, idesc, acc0);
+                    else issue_dispatch<NPASS, false>(nk, acc, 0, 0, ahi, alo, dhi, dlo, idesc, acc0);
                     umma_commit(&bars->mma_done[t][net]);
                     if (t == ntile - 1) umma_commit(&bars->empty[it & smask]);   // all tiles' MMAs done -> slot free
                 }
@@ -443,7 +482,7 @@ __device__ __forceinline__ void t3_issuer(const T2Step* __restrict__ steps, cons
 // INV: the sampler (flow.sample_with_log_prob, fastpredNF.py:586-607): every step runs CIF_step.inverse -- sample u from
 // q, undo the blocks last to first, score u under r -- and the point / prefix come from the row's own samples.
 // MODE (compile-time copy of T3Dims::seq for this role): 0 per-step density, 1 chain, 2 sampler
-template <int NPASS, bool FOLD_D, bool FOLD_C, int MODE>
+template <int NPASS, bool FOLD_D, bool FOLD_C, int MODE, bool HTS>
 __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, const RowArgs& a, const SampleOut& o, const T3Dims& dm,
                                         long long pairs_per_step, long long total_items, uint8_t* smem, uint32_t tmem_base) {
     constexpr int NPARTS = 2;
@@ -489,8 +528,7 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
             base_lp = normal_lp2(z0, z1, prev0, prev1, s0, s1);
             if (valid && x.part == 0) o.base_lp[n] = base_lp;
         } else {
-            const float* xp = src_at(a.x, ag, pt, jstep);
-            z0 = __ldg(xp); z1 = __ldg(xp + 1);
+            load_query(a, ag, pt, jstep, z0, z1);
             // base mean: per-step mode = previous trajectory point; chain mode = base_pos (fastpredNF.py:454-458)
             const float* pp = (MODE == 1 || jstep == 0) ? src_at(a.base, ag, pt, 0) : src_at(a.prefix, ag, pt, jstep - 1);
             prev0 = __ldg(pp); prev1 = __ldg(pp + 1);
@@ -501,6 +539,10 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
         // byte offset of this row inside a canonical [128 x W] operand tile, for the two hidden widths of the step
         const uint32_t koff_d = (uint32_t)((x.row >> 3) * (Wd >> 3) * 128 + (x.row & 7) * 16);
         const uint32_t koff_c = (uint32_t)((x.row >> 3) * (Hc >> 3) * 128 + (x.row & 7) * 16);
+        // HTS: shared addresses of this row inside the first-layer operand tiles [IN hi, IN lo, U hi, U lo] of its tile
+        const uint32_t in_row = x.h_base + (uint32_t)((x.row >> 3) * (Kin >> 3) * 128 + (x.row & 7) * 16);
+        const uint32_t u_row = x.h_base + 2u * h_stride + (uint32_t)((x.row >> 3) * (Ku >> 3) * 128 + (x.row & 7) * 16);
+        constexpr uint32_t kAcc1 = HTS ? kT3HAcc1 : kT3Acc1;
         // ---- input operand [z (2), cond (C0), prefix (2*step), 0...] ----
         {
             const float* cp = src_at(a.cond, ag, pt, INV ? step : jstep) - 2;     // chain mode: cond[:, j] for every chain step
@@ -522,8 +564,13 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
                 }
                 uint32_t hi[4], lo[4];
                 split8<NPASS, false>(v, hi, lo);
-                tmem_st4(x.tb + kT3InHi + (uint32_t)(k0 >> 1), hi);
-                if (NPASS == 3) tmem_st4(x.tb + kT3InLo + (uint32_t)(k0 >> 1), lo);
+                if (HTS) {
+                    sts128(in_row + (uint32_t)(k0 >> 3) * 128u, hi);
+                    if (NPASS == 3) sts128(in_row + h_stride + (uint32_t)(k0 >> 3) * 128u, lo);
+                } else {
+                    tmem_st4(x.tb + kT3InHi + (uint32_t)(k0 >> 1), hi);
+                    if (NPASS == 3) tmem_st4(x.tb + kT3InLo + (uint32_t)(k0 >> 1), lo);
+                }
             }
         }
         warp_arrive3(x, &bars->fin[g]);
@@ -533,18 +580,36 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
             // ============ density nets (shift | log-scale): two relu layers ============
 #pragma unroll 1
             for (int l = 0; l < 2; ++l) {
+#if FC_T3_SPLIT_NETS
+                {
+                    const int net = x.part;
+                    const uint32_t bias = x.bias_ring + (uint32_t)(net * 4 + ((x.chunk_it >> 1) & 3)) * kT3BiasEntry;
+                    T3_TR(0x10 + net)
+                    wait_mma3(x, 0);         // every thread tracks both nets' phases; the other net's MMAs were issued earlier
+                    wait_mma3(x, 1);
+                    T3_TR(0x12 + net)
+                    const uint32_t acc = x.tb + (net ? kAcc1 : kT3Acc0);
+                    const uint32_t ohi = HTS ? x.tb + (net ? kT3H1Hi : kT3H0Hi) : x.h_base + (uint32_t)(net * 2) * h_stride;
+                    const uint32_t olo = HTS ? x.tb + (net ? kT3H1Lo : kT3H0Lo) : ohi + h_stride;
+                    epi_layer3<NPASS, ACT_R, false, true, !FOLD_D, HTS>(acc, ohi, olo, bias, 0u, x.part, Wd, koff_d);
+                    warp_arrive3(x, &bars->opnd[g][net]);
+                    x.chunk_it += 2;
+                }
+#else
 #pragma unroll 1
                 for (int net = 0; net < 2; ++net) {
                     const uint32_t bias = x.bias_ring + (uint32_t)(net * 4 + ((x.chunk_it >> 1) & 3)) * kT3BiasEntry;
                     T3_TR(0x10 + net)        // waiting for the MMAs of this net
                     wait_mma3(x, net);
                     T3_TR(0x12 + net)        // accumulator ready: epilogue starts
-                    const uint32_t acc = x.tb + (net ? kT3Acc1 : kT3Acc0);
-                    const uint32_t ohi = x.h_base + (uint32_t)(net * 2) * h_stride, olo = ohi + h_stride;
-                    epi_layer3<NPASS, ACT_R, false, true, !FOLD_D>(acc, ohi, olo, bias, 0u, x.part, Wd, koff_d);
+                    const uint32_t acc = x.tb + (net ? kAcc1 : kT3Acc0);
+                    const uint32_t ohi = HTS ? x.tb + (net ? kT3H1Hi : kT3H0Hi) : x.h_base + (uint32_t)(net * 2) * h_stride;
+                    const uint32_t olo = HTS ? x.tb + (net ? kT3H1Lo : kT3H0Lo) : ohi + h_stride;
+                    epi_layer3<NPASS, ACT_R, false, true, !FOLD_D, HTS>(acc, ohi, olo, bias, 0u, x.part, Wd, koff_d);
                     warp_arrive3(x, &bars->opnd[g][net]);
                     x.chunk_it++;
                 }
+#endif
             }
             // ---- L3 outputs: means in acc0[0,CPd), log-stddevs in acc1[0,CPd) ----
             const float* bias_mu = reinterpret_cast<const float*>(bias_ring + (size_t)(0 * 4 + ((x.chunk_it >> 1) & 3)) * kT3BiasEntry);
@@ -573,7 +638,7 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
 #pragma unroll
                         for (int i = 0; i < 8; ++i) e[i] = 0.0f;
                         tmem_ld8(x.tb + kT3Acc0 + (uint32_t)d0, mu);
-                        tmem_ld8(x.tb + kT3Acc1 + (uint32_t)d0, ls);
+                        tmem_ld8(x.tb + kAcc1 + (uint32_t)d0, ls);
                         if (a.eps != nullptr) {
                             const float* ep = a.eps + n * a.eps_rs + (MODE == 1 ? ts.seq_eps_off + (jstep - step) * C : ts.eps_off) + d0;
 #pragma unroll
@@ -601,8 +666,13 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
                     }
                     uint32_t hi[4], lo[4];
                     split8<3, false>(u, hi, lo);     // u is always kept as a hi+lo pair: log q needs it back at full precision
-                    tmem_st4(x.tb + kT3UHi + (uint32_t)(d0 >> 1), hi);
-                    tmem_st4(x.tb + kT3ULo + (uint32_t)(d0 >> 1), lo);
+                    if (HTS) {
+                        sts128(u_row + (uint32_t)(d0 >> 3) * 128u, hi);
+                        sts128(u_row + h_stride + (uint32_t)(d0 >> 3) * 128u, lo);
+                    } else {
+                        tmem_st4(x.tb + kT3UHi + (uint32_t)(d0 >> 1), hi);
+                        tmem_st4(x.tb + kT3ULo + (uint32_t)(d0 >> 1), lo);
+                    }
                 }
                 const float s_ls = row_sum3(x, 0, p_ls), s_e2 = row_sum3(x, 1, p_e2);
                 const float lp_u = (-0.5f * (float)C * kLog2Pi - s_ls) - 0.5f * s_e2;      // log density of the drawn u
@@ -614,9 +684,14 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
                     float mu[8], ls[8];
                     uint32_t uh[4], ul[4];
                     tmem_ld8(x.tb + kT3Acc0 + (uint32_t)d0, mu);
-                    tmem_ld8(x.tb + kT3Acc1 + (uint32_t)d0, ls);
-                    tmem_ld4(x.tb + kT3UHi + (uint32_t)(d0 >> 1), uh);
-                    tmem_ld4(x.tb + kT3ULo + (uint32_t)(d0 >> 1), ul);
+                    tmem_ld8(x.tb + kAcc1 + (uint32_t)d0, ls);
+                    if (HTS) {
+                        lds128u(u_row + (uint32_t)(d0 >> 3) * 128u, uh);
+                        lds128u(u_row + h_stride + (uint32_t)(d0 >> 3) * 128u, ul);
+                    } else {
+                        tmem_ld4(x.tb + kT3UHi + (uint32_t)(d0 >> 1), uh);
+                        tmem_ld4(x.tb + kT3ULo + (uint32_t)(d0 >> 1), ul);
+                    }
                     tmem_wait_ld();
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -648,6 +723,31 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
 #pragma unroll 1
                 for (int l = 0; l <= ts.n_hidden; ++l) {
                     const bool last = l == ts.n_hidden;
+#if FC_T3_SPLIT_NETS
+                    {
+                        const int net = x.part;
+                        const uint32_t tail = x.bias_ring + (uint32_t)(net * 4 + ((x.chunk_it >> 1) & 3)) * kT3BiasEntry;
+                        x.chunk_it += 2;
+                        T3_TR(0x10 + net)
+                        wait_mma3(x, 0);
+                        wait_mma3(x, 1);
+                        T3_TR(0x12 + net)
+                        const uint32_t acc = x.tb + (net ? kAcc1 : kT3Acc0);
+                        const uint32_t ohi = HTS ? x.tb + (net ? kT3H1Hi : kT3H0Hi) : x.h_base + (uint32_t)(net * 2) * h_stride;
+                        const uint32_t olo = HTS ? x.tb + (net ? kT3H1Lo : kT3H0Lo) : ohi + h_stride;
+                        if (!last) {
+                            if (net == 0) epi_layer3<NPASS, ACT_T, false, true, !FOLD_C, HTS>(acc, ohi, olo, tail, 0u, x.part, Hc, koff_c);
+                            else epi_layer3<NPASS, ACT_R, false, true, !FOLD_C, HTS>(acc, ohi, olo, tail, 0u, x.part, Hc, koff_c);
+                            warp_arrive3(x, &bars->opnd[g][net]);
+                        } else {
+                            float pd;
+                            if (net == 0) pd = epi_layer3<NPASS, ACT_T, true, false, !FOLD_C>(acc, ohi, olo, tail, tail + Hc * 4, x.part, Hc, koff_c);
+                            else pd = epi_layer3<NPASS, ACT_R, true, false, !FOLD_C>(acc, ohi, olo, tail, tail + Hc * 4, x.part, Hc, koff_c);
+                            // this part owns the whole dot product of its net: its bias rides in the partial (the other part adds 0)
+                            if (net == 0) ps = pd + lds32(tail + Hc * 8); else pt_ = pd + lds32(tail + Hc * 8);
+                        }
+                    }
+#else
 #pragma unroll 1
                     for (int net = 0; net < 2; ++net) {
                         const uint32_t tail = x.bias_ring + (uint32_t)(net * 4 + ((x.chunk_it >> 1) & 3)) * kT3BiasEntry;
@@ -655,11 +755,12 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
                         T3_TR(0x10 + net)
                         wait_mma3(x, net);
                         T3_TR(0x12 + net)
-                        const uint32_t acc = x.tb + (net ? kT3Acc1 : kT3Acc0);
-                        const uint32_t ohi = x.h_base + (uint32_t)(net * 2) * h_stride, olo = ohi + h_stride;
+                        const uint32_t acc = x.tb + (net ? kAcc1 : kT3Acc0);
+                        const uint32_t ohi = HTS ? x.tb + (net ? kT3H1Hi : kT3H0Hi) : x.h_base + (uint32_t)(net * 2) * h_stride;
+                        const uint32_t olo = HTS ? x.tb + (net ? kT3H1Lo : kT3H0Lo) : ohi + h_stride;
                         if (!last) {
-                            if (net == 0) epi_layer3<NPASS, ACT_T, false, true, !FOLD_C>(acc, ohi, olo, tail, 0u, x.part, Hc, koff_c);
-                            else epi_layer3<NPASS, ACT_R, false, true, !FOLD_C>(acc, ohi, olo, tail, 0u, x.part, Hc, koff_c);
+                            if (net == 0) epi_layer3<NPASS, ACT_T, false, true, !FOLD_C, HTS>(acc, ohi, olo, tail, 0u, x.part, Hc, koff_c);
+                            else epi_layer3<NPASS, ACT_R, false, true, !FOLD_C, HTS>(acc, ohi, olo, tail, 0u, x.part, Hc, koff_c);
                             warp_arrive3(x, &bars->opnd[g][net]);
                         } else {
                             float pd;
@@ -668,6 +769,7 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
                             if (net == 0) { ps = pd; bs = lds32(tail + Hc * 8); } else { pt_ = pd; bt = lds32(tail + Hc * 8); }
                         }
                     }
+#endif
                 }
                 // both nets done: affine update of the unmasked coordinate + BatchNorm (TFCondARFlow.py:360-381, 303-315)
                 const float s = row_sum3(x, 0, ps) + bs, t = row_sum3(x, 1, pt_) + bt;
@@ -689,24 +791,31 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
                     }
                 }
                 float p0, p1;
-                uint32_t dst_hi, dst_lo;
+                uint32_t dst_hi, dst_lo;      // HTS: shared addresses of the (hi, lo) pair; otherwise tensor-memory columns
                 int owner;
                 if (more) {
                     const int mn = ts.masked_dim[bn];
                     p0 = mn == 0 ? clamp_h(z0) : 0.0f; p1 = mn == 1 ? clamp_h(z1) : 0.0f;
-                    dst_hi = kT3UHi + (uint32_t)(C >> 1); dst_lo = kT3ULo + (uint32_t)(C >> 1);
+                    if (HTS) { dst_hi = u_row + (uint32_t)(C >> 3) * 128u + (uint32_t)(C & 7) * 2u; dst_lo = dst_hi + h_stride; }
+                    else { dst_hi = kT3UHi + (uint32_t)(C >> 1); dst_lo = kT3ULo + (uint32_t)(C >> 1); }
                     owner = (C >> 3) % NPARTS;
                 } else {
                     p0 = clamp_h(z0); p1 = clamp_h(z1);
-                    dst_hi = kT3InHi; dst_lo = kT3InLo;
+                    if (HTS) { dst_hi = in_row; dst_lo = in_row + h_stride; }
+                    else { dst_hi = kT3InHi; dst_lo = kT3InLo; }
                     owner = 0;
                 }
                 if (x.part == owner) {
                     const __half2 h = __floats2half2_rn(p0, p1);
                     const float2 f = __half22float2(h);
                     const __half2 lo2 = __floats2half2_rn(p0 - f.x, p1 - f.y);
-                    tmem_st1(x.tb + dst_hi, *reinterpret_cast<const uint32_t*>(&h));
-                    tmem_st1(x.tb + dst_lo, *reinterpret_cast<const uint32_t*>(&lo2));
+                    if (HTS) {
+                        sts32(dst_hi, *reinterpret_cast<const uint32_t*>(&h));
+                        sts32(dst_lo, *reinterpret_cast<const uint32_t*>(&lo2));
+                    } else {
+                        tmem_st1(x.tb + dst_hi, *reinterpret_cast<const uint32_t*>(&h));
+                        tmem_st1(x.tb + dst_lo, *reinterpret_cast<const uint32_t*>(&lo2));
+                    }
                 }
                 warp_arrive3(x, &bars->fin[g]);
             }
@@ -735,7 +844,7 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
 
 }  // namespace t3
 
-template <int NPASS, bool FOLD_D, bool FOLD_C, int MODE = 0>
+template <int NPASS, bool FOLD_D, bool FOLD_C, int MODE = 0, bool HTS = false>
 __global__ void __launch_bounds__(kT3Threads, 1)
 k_separate_tc3(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img, const __grid_constant__ RowArgs a,
                const __grid_constant__ T3Dims dm, long long pairs_per_step, long long total_items, const __grid_constant__ SampleOut o) {
@@ -756,8 +865,8 @@ k_separate_tc3(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
         for (int t = 0; t < 2; ++t) {
             mbar_init(&bars->mma_done[t][0], 1);
             mbar_init(&bars->mma_done[t][1], 1);
-            mbar_init(&bars->opnd[t][0], 8);
-            mbar_init(&bars->opnd[t][1], 8);
+            mbar_init(&bars->opnd[t][0], FC_T3_SPLIT_NETS ? 4 : 8);      // warps that run this net's hidden epilogues
+            mbar_init(&bars->opnd[t][1], FC_T3_SPLIT_NETS ? 4 : 8);
             mbar_init(&bars->fin[t], 8);
         }
         mbar_fence_init();
@@ -782,11 +891,11 @@ k_separate_tc3(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
     // setmaxnreg.inc only draws on what .dec released: 4 x 128 x (104 - 96) = 4096 <= 128 x (96 - 56) = 5120.
     if (warp < 16) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kT3ComputeRegs));
-        t3_compute<NPASS, FOLD_D, FOLD_C, MODE>(steps, a, o, dm, pairs_per_step, total_items, smem, tmem_base);
+        t3_compute<NPASS, FOLD_D, FOLD_C, MODE, HTS>(steps, a, o, dm, pairs_per_step, total_items, smem, tmem_base);
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kT3ServiceRegs));
         if (warp == 16) t3_producer(steps, img, dm, pairs_per_step, total_items, smem);
-        else if (warp < 19) t3_issuer<NPASS>(steps, dm, pairs_per_step, total_items, smem, tmem_base, warp - 17);
+        else if (warp < 19) t3_issuer<NPASS, HTS>(steps, dm, pairs_per_step, total_items, smem, tmem_base, warp - 17);
         else t3_idle(steps, dm, pairs_per_step, total_items, smem);
     }
 
@@ -840,9 +949,12 @@ inline int tc3_launch_separate(const T2Dims& dm2, const std::vector<T2Step>& hst
         for (int s = lo; s <= hi; ++s)
             for (int ci = 0; ci < hsteps[s].nchunks; ++ci) slot = hsteps[s].chunk_bytes[ci] > slot ? hsteps[s].chunk_bytes[ci] : slot;
         slot = (slot + 127) / 128 * 128;
+        // steps whose layers are all <= 64 wide: hidden operands in tensor memory, first-layer operands (K <= 32) in smem
+        bool hts = wc == 64 && fold_d && fold_c;
+        for (int s = lo; s <= hi; ++s) hts = hts && hsteps[s].Kin <= kT3InuK && hsteps[s].Ku <= kT3InuK;
         T3Dims dm{};
-        dm.slot_bytes = slot; dm.Wmax = wc; dm.T = T; dm.C0 = dm2.C0; dm.step_lo = lo; dm.step_hi = hi; dm.single = single ? 1 : 0;
-        const size_t fixed = (size_t)kT3Header + (size_t)8 * 128 * wc * 2;
+        dm.slot_bytes = slot; dm.Wmax = hts ? kT3InuK : wc; dm.T = T; dm.C0 = dm2.C0; dm.step_lo = lo; dm.step_hi = hi; dm.single = single ? 1 : 0;
+        const size_t fixed = (size_t)kT3Header + (size_t)8 * 128 * dm.Wmax * 2;
         // a weight slot is handed back by the tcgen05.commit of the MMAs that read it, so 2 slots (one per net) already
         // pipeline; 4 when they fit
         dm.nslots_log2 = (fixed + (size_t)4 * slot <= (size_t)smem_optin) ? 2 : 1;
@@ -855,7 +967,12 @@ inline int tc3_launch_separate(const T2Dims& dm2, const std::vector<T2Step>& hst
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e == cudaSuccess) kern<<<grid, kT3Threads, smem, stream>>>(d_steps, d_img, a, dm, pairs, items, SampleOut{});
         };
-        if (fold_d && fold_c) go(k_separate_tc3<NPASS, true, true>);
+#ifdef FC_T3_HTS_NOFOLD
+        if (hts) { dm.no_fold = 1; go(k_separate_tc3<NPASS, false, false, 0, true>); }
+#else
+        if (hts) go(k_separate_tc3<NPASS, true, true, 0, true>);
+#endif
+        else if (fold_d && fold_c) go(k_separate_tc3<NPASS, true, true>);
         else if (fold_c) go(k_separate_tc3<NPASS, false, true>);
         else if (fold_d) go(k_separate_tc3<NPASS, true, false>);
         else go(k_separate_tc3<NPASS, false, false>);

@@ -463,8 +463,7 @@ __device__ __forceinline__ void tw_compute(const TwStep* __restrict__ steps, con
             base_lp = normal_lp2(z0, z1, prev0, prev1, s0, s1);
             if (valid && x.part == 0) o.base_lp[n] = base_lp;
         } else {
-            const float* xp = src_at(a.x, ag, pt, jstep);
-            z0 = __ldg(xp); z1 = __ldg(xp + 1);
+            load_query(a, ag, pt, jstep, z0, z1);
             // base mean: per-step mode = previous trajectory point; chain mode = base_pos (fastpredNF.py:454-458)
             const float* pp = (MODE == 1 || jstep == 0) ? src_at(a.base, ag, pt, 0) : src_at(a.prefix, ag, pt, jstep - 1);
             prev0 = __ldg(pp); prev1 = __ldg(pp + 1);

@@ -68,6 +68,15 @@ struct RowArgs {
     int seq_jlo;           // sequential: first result index written (0, or T - n_step - 1)
     int fuse_k;            // 1: K = 2^j <= 32 importance samples of a point sit in consecutive rows (= lanes): logsumexp_k - log K
                            // is reduced with warp shuffles in registers and ONE value per (point, step) is stored
+    // position-space density maps (per-step density with a shared prefix only): the query of row
+    // (agent, point) at step t is z = (x[point] - qshift[agent, t]) * qscale[agent] -- the caller's METRIC lattice mapped
+    // into the standardised state space of that agent and step -- and every result of the agent gets out_shift[agent]
+    // (the log-Jacobian of that change of variables) added and, with out_exp, is stored as exp(.) (a probability density)
+    const float* qshift;   // (A, T, 2) or nullptr
+    long long qshift_sa, qshift_st;
+    const float* qscale;   // (A, 2) or nullptr
+    const float* out_shift;   // (A) or nullptr
+    int out_exp;
     int out_sys;           // 1: `out` is an NVSwitch multicast address of a symmetric buffer: every store is replicated to
                            // all peers, so the density maps are all-gathered by the stores themselves (multimem.st, system scope)
 };
@@ -78,6 +87,20 @@ __device__ __forceinline__ void store_out(const RowArgs& a, long long idx, float
     // multicast (multimem) addresses may only be accessed with multimem.* instructions (PTX ISA, "multimem.st")
     if (a.out_sys) asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(a.out + idx), "f"(v) : "memory");
     else a.out[idx] = v;
+}
+// query point of row (agent, point) at `step` (see RowArgs::qscale)
+__device__ __forceinline__ void load_query(const RowArgs& a, long long ag, long long pt, int step, float& z0, float& z1) {
+    const float* xp = a.x.p + ag * a.x.sa + pt * a.x.sp + (long long)step * a.x.st;
+    z0 = __ldg(xp); z1 = __ldg(xp + 1);
+    if (a.qscale != nullptr) {
+        const float* qs = a.qshift + ag * a.qshift_sa + (long long)step * a.qshift_st;
+        z0 = (z0 - __ldg(qs)) * __ldg(a.qscale + ag * 2);
+        z1 = (z1 - __ldg(qs + 1)) * __ldg(a.qscale + ag * 2 + 1);
+    }
+}
+__device__ __forceinline__ float finish_out(const RowArgs& a, long long ag, float v) {
+    if (a.out_shift != nullptr) v += __ldg(a.out_shift + ag);
+    return a.out_exp ? expf(v) : v;
 }
 // Result of row (agent ag, point-row rem = n % PPA) at output step `tidx`.  Must be reached by all 32 lanes of the warp
 // (rows are consecutive lanes; `valid` masks rows past N).  K > 1 fused: CIF importance-sample bound
@@ -90,10 +113,10 @@ __device__ __forceinline__ void store_result(const RowArgs& a, long long ag, lon
         for (int o = 1; o < a.K; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (valid && (rem % a.K) == 0) {
             const float v = (m == -INFINITY) ? -INFINITY : m + logf(s) - logf((float)a.K);
-            store_out(a, ag * a.out_sa + (rem / a.K) * a.out_sp + tidx * a.out_st, v);
+            store_out(a, ag * a.out_sa + (rem / a.K) * a.out_sp + tidx * a.out_st, finish_out(a, ag, v));
         }
     } else if (valid) {
-        store_out(a, ag * a.out_sa + rem * a.out_sp + tidx * a.out_st, lp);
+        store_out(a, ag * a.out_sa + rem * a.out_sp + tidx * a.out_st, finish_out(a, ag, lp));
     }
 }
 #endif

@@ -138,6 +138,101 @@ class fastpredNF_TP(nn.Module):
         data_dict[("prob_st", 0)] = torch.cat([seq, lp[..., None]], dim=-1)
         return data_dict
 
+    # ---- consumers right after the hot path -----------------------------------------------
+    _STATE_MODE = {"state_p": 0, "state_v": 1}
+
+    def _state_mode(self) -> int:
+        if self.pred_state not in self._STATE_MODE:
+            raise AssertionError("acceleration states are not supported (the reference asserts the same, TP_metrics.py:70,94)")
+        return self._STATE_MODE[self.pred_state]
+
+    def _f32(self, t):
+        return None if t is None else torch.as_tensor(t).to(self.flow.var.device, torch.float32).contiguous()
+
+    @torch.no_grad()
+    def denormalize(self, data_dict: Dict, std) -> Dict:
+        """TP_metrics.denormalize for one data_dict (src/metrics/TP_metrics.py:62-112), fused on the device:
+        ("pred", 0) = metric trajectory of ("pred_st", 0); `gt` (un-standardised state) -> metric positions;
+        every ("prob_st", k) -> ("prob", k) = [metric positions, p = exp(log p)].  `std` = the dataset's standardisation
+        scale (2,), `data_dict["dt"]` (B,), `data_dict["obs"][:, -1, :2]` = last observed metric position."""
+        if ("pred", 0) in data_dict:
+            return data_dict
+        h = self.flow.engine()
+        mode = self._state_mode()
+        s0, s1 = (float(v) for v in torch.as_tensor(std).flatten()[:2])
+        last_obs = self._f32(data_dict["obs"][:, -1, 0:2])
+        dt = self._f32(data_dict["dt"]) if mode == 1 else None
+        pred = self._f32(data_dict[("pred_st", 0)])
+        data_dict[("pred", 0)] = torch.ops.flowchain.to_trajectories(h.id, pred[:, None], last_obs, dt, s0, s1, mode)[:, 0]
+        if mode == 1:       # the un-standardised ground-truth velocities become positions (TP_metrics.py:82-83)
+            gt_v = self._f32(data_dict["gt"])
+            data_dict["gt"] = torch.ops.flowchain.to_trajectories(h.id, gt_v[:, None], last_obs, dt, 1.0, 1.0, 1)[:, 0]
+        gt_pos = self._f32(data_dict["gt"])
+        for k in [k for k in data_dict if isinstance(k, tuple) and k[0] == "prob_st" and isinstance(data_dict[k], torch.Tensor)]:
+            off = last_obs if k[1] == 0 else gt_pos[:, k[1] - 1].contiguous()
+            data_dict[("prob", k[1])] = torch.ops.flowchain.to_trajectories(h.id, self._f32(data_dict[k]), off, dt, s0, s1, mode)
+        return data_dict
+
+    @torch.no_grad()
+    def prob_to_grid(self, data_dict: Dict, xx, yy, std, cond_traj="gt", as_prob: bool = True, **kw) -> Dict:
+        """Drop-in for TP_visualizer.prob_to_grid on FlowChain outputs (src/visualization/TP_visualizer.py:118-179): sets
+        `grid`, ("prob", 0) = (B, G, T) density on the metric lattice (xx, yy) (flattened like `zz.reshape(-1, T)`) and
+        ("gt_traj_log_prob", 0) (B, T).  The reference scatters 10 000 sampled (position, p) pairs per step and
+        interpolates them on the CPU (single-linkage clustering + griddata + RBF), then reads the ground truth off the
+        lattice with interp2d; here the analytic per-step density is evaluated directly: on the lattice, conditioned on
+        a prefix trajectory (`cond_traj`: "gt" = teacher forcing with data_dict["gt_st"], or a (B,T,2) standardised
+        tensor such as the ML prediction), and exactly at the ground truth.  Both are proper densities in metric space."""
+        h = self.flow.engine()
+        dev = self.flow.var.device
+        mode = self._state_mode()
+        stdv = torch.as_tensor(std, dtype=torch.float32, device=dev).flatten()[:2]
+        dist_args = self._f32(self.encoder(data_dict))
+        base_pos = self._f32(self.get_base_pos(data_dict))
+        traj = self._f32(data_dict["gt_st"] if isinstance(cond_traj, str) else cond_traj)
+        B, T = traj.shape[0], traj.shape[1]
+        last_obs = self._f32(data_dict["obs"][:, -1, 0:2])
+        if mode == 1:
+            dt = self._f32(data_dict["dt"])
+            step = traj * stdv * dt[:, None, None]                                  # metric displacement of every step
+            origin = last_obs[:, None] + torch.cumsum(step, dim=1) - step           # position BEFORE step t
+            inv_scale = 1.0 / (stdv[None] * dt[:, None])
+        else:
+            origin = last_obs[:, None].expand(B, T, 2)
+            inv_scale = (1.0 / stdv)[None].expand(B, 2)
+        log_jac = torch.log(inv_scale).sum(-1)                                      # log |d state / d position|
+        grid_xy = torch.stack([torch.as_tensor(xx, dtype=torch.float32).flatten(),
+                               torch.as_tensor(yy, dtype=torch.float32).flatten()], dim=-1).to(dev).contiguous()
+        eps, seed = kw.pop("eps", None), kw.pop("seed", None)
+        prec = kw.pop("precision", None)
+        maps = torch.ops.flowchain.grid_density_maps(
+            h.id, base_pos, dist_args, traj, grid_xy, origin.contiguous(), inv_scale.contiguous(), log_jac.contiguous(),
+            self._f32(eps), 0 if eps is not None else self.flow._seed(seed), bool(as_prob), False,
+            self.flow.precision if prec is None else prec)
+        data_dict["grid"] = [xx, yy]
+        data_dict[("prob", 0)] = maps
+        if "gt_st" in data_dict:
+            lp = self.flow.log_prob(base_pos, self._f32(data_dict["gt_st"]), dist_args, eps=kw.pop("eps_gt", None), seed=seed,
+                                    precision=prec)
+            data_dict[("gt_traj_log_prob", 0)] = lp + log_jac[:, None]
+        return data_dict
+
+    @torch.no_grad()
+    def predict_best_of_n(self, data_dict: Dict, std, n_trial: int = 20, **noise) -> Dict:
+        """The ADE/FDE best-of-N evaluation of src/main.py:162-180 in one go: ONE sampler launch with S = n_trial
+        candidates per agent (the reference runs n_trial predict() calls of 100 samples each and keeps the last sample
+        of each, fastpredNF.py:123-140) + an on-device un-standardise / cumsum / min-reduction.  `data_dict["gt"]` must
+        hold METRIC ground-truth positions (B,T,2).  Returns per-agent minima and their sums (evaluate_helper)."""
+        h = self.flow.engine()
+        mode = self._state_mode()
+        s0, s1 = (float(v) for v in torch.as_tensor(std).flatten()[:2])
+        seq, _, _, _ = self._sample(data_dict, n_trial, **noise)                    # (B, n_trial, T, 2)
+        fallback = self._f32(data_dict["obs_st"][:, 0, 2:4])
+        ade, fde, ia, jf = torch.ops.flowchain.best_of_n(
+            h.id, self._f32(seq), self._f32(data_dict["gt"]), self._f32(data_dict["obs"][:, -1, 0:2]),
+            self._f32(data_dict["dt"]) if mode == 1 else None, fallback, s0, s1, mode)
+        return {"ade": ade.sum(), "fde": fde.sum(), "ade_per_agent": ade, "fde_per_agent": fde, "ade_arg": ia, "fde_arg": jf,
+                "nsample": ade.shape[0], "candidates_st": seq}
+
     def gt_log_prob(self, data_dict: Dict, **kw) -> torch.Tensor:
         """Exact log p of the ground-truth future under the per-step density: flow.log_prob(base_pos, gt_st, cond) -> (B, T).
         Replaces the visualiser's detour of interpolating a KDE of samples on a grid and reading it off at the GT

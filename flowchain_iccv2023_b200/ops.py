@@ -275,3 +275,85 @@ def update_lazy(hid: int, new_pos: torch.Tensor, time_step: int, prob_st_0: torc
 @update_lazy.register_fake
 def _(hid, new_pos, time_step, prob_st_0, normalizer):
     return prob_st_0.new_empty((prob_st_0.shape[0], prob_st_0.shape[1]))
+
+
+# ------------------------------------------------------------------------------------------------
+# consumers right after the hot path
+# ------------------------------------------------------------------------------------------------
+
+@torch.library.custom_op("flowchain::grid_density_maps", mutates_args=())
+def grid_density_maps(hid: int, base_pos: torch.Tensor, cond: torch.Tensor, cond_traj: torch.Tensor, grid_xy: torch.Tensor,
+                      origin: torch.Tensor, inv_scale: torch.Tensor, log_jac: Optional[torch.Tensor],
+                      eps: Optional[torch.Tensor], seed: int, as_prob: bool, map_layout: bool, precision: int) -> torch.Tensor:
+    """Per-step density on a METRIC lattice: out[a,g,t] = p_t((grid_xy[g] - origin[a,t]) * inv_scale[a] | cond_traj[a,:t])
+    * exp(log_jac[a]) (or its log).  (A, G, T), or (A, T, G) with map_layout."""
+    h = _h(hid)
+    s = h.spec
+    A, G, T = base_pos.shape[0], grid_xy.shape[0], s.pred_len
+    if map_layout:
+        out = torch.empty((A, T, G), dtype=torch.float32, device=grid_xy.device)
+        sa, sp, st = T * G, 1, G
+    else:
+        out = torch.empty((A, G, T), dtype=torch.float32, device=grid_xy.device)
+        sa, sp, st = G * T, T, 1
+    rc = _lib.load().fc_grid_density_maps(
+        h.ptr, _chk(base_pos, (A, 2), "base_pos", h), _chk(cond, (A, T, s.cond_size), "cond", h),
+        _chk(cond_traj, (A, T, 2), "cond_traj", h), _chk(grid_xy, (G, 2), "grid_xy", h), _chk(origin, (A, T, 2), "origin", h),
+        _chk(inv_scale, (A, 2), "inv_scale", h), _chk(log_jac, (A,), "log_jac", h), _chk(eps, (A * G, h.E), "eps", h),
+        seed, int(as_prob), out.data_ptr(), sa, sp, st, A, G, precision, _stream(h))
+    h.check(rc, "fc_grid_density_maps")
+    return out
+
+
+@grid_density_maps.register_fake
+def _(hid, base_pos, cond, cond_traj, grid_xy, origin, inv_scale, log_jac, eps, seed, as_prob, map_layout, precision):
+    A, G, T = base_pos.shape[0], grid_xy.shape[0], cond.shape[1]
+    return grid_xy.new_empty((A, T, G) if map_layout else (A, G, T))
+
+
+@torch.library.custom_op("flowchain::to_trajectories", mutates_args=())
+def to_trajectories(hid: int, state_st: torch.Tensor, offset: torch.Tensor, dt: Optional[torch.Tensor], std0: float, std1: float,
+                    state_mode: int) -> torch.Tensor:
+    """TP_metrics.unstandardize + output_to_trajectories for one (A, S, Tk, 2|3) tensor (see fc_to_trajectories)."""
+    h = _h(hid)
+    if state_st.dim() != 4 or state_st.shape[-1] not in (2, 3):
+        raise RuntimeError(f"state_st: expected (A, S, Tk, 2|3), got {tuple(state_st.shape)}")
+    A, S, Tk, ncol = state_st.shape
+    out = torch.empty_like(state_st)
+    rc = _lib.load().fc_to_trajectories(
+        h.ptr, _chk(state_st, None, "state_st", h), _chk(offset, (A, 2), "offset", h), _chk(dt, (A,), "dt", h),
+        float(std0), float(std1), state_mode, out.data_ptr(), A, S, Tk, ncol, _stream(h))
+    h.check(rc, "fc_to_trajectories")
+    return out
+
+
+@to_trajectories.register_fake
+def _(hid, state_st, offset, dt, std0, std1, state_mode):
+    return torch.empty_like(state_st)
+
+
+@torch.library.custom_op("flowchain::best_of_n", mutates_args=())
+def best_of_n(hid: int, cand_st: torch.Tensor, gt: torch.Tensor, last_obs: torch.Tensor, dt: Optional[torch.Tensor],
+              fallback_st: Optional[torch.Tensor], std0: float, std1: float,
+              state_mode: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Per-agent best-of-N ADE / FDE with the winning candidate indices (see fc_best_of_n)."""
+    h = _h(hid)
+    A, N, T, _ = cand_st.shape
+    dev = cand_st.device
+    ade = torch.empty((A,), dtype=torch.float32, device=dev)
+    fde = torch.empty((A,), dtype=torch.float32, device=dev)
+    ia = torch.empty((A,), dtype=torch.int32, device=dev)
+    jf = torch.empty((A,), dtype=torch.int32, device=dev)
+    rc = _lib.load().fc_best_of_n(
+        h.ptr, _chk(cand_st, (A, N, T, 2), "cand_st", h), _chk(gt, (A, T, 2), "gt", h), _chk(last_obs, (A, 2), "last_obs", h),
+        _chk(dt, (A,), "dt", h), _chk(fallback_st, (A, 2), "fallback_st", h), float(std0), float(std1), state_mode,
+        ade.data_ptr(), fde.data_ptr(), ia.data_ptr(), jf.data_ptr(), A, N, T, _stream(h))
+    h.check(rc, "fc_best_of_n")
+    return ade, fde, ia, jf
+
+
+@best_of_n.register_fake
+def _(hid, cand_st, gt, last_obs, dt, fallback_st, std0, std1, state_mode):
+    A = cand_st.shape[0]
+    return (cand_st.new_empty((A,)), cand_st.new_empty((A,)), cand_st.new_empty((A,), dtype=torch.int32),
+            cand_st.new_empty((A,), dtype=torch.int32))

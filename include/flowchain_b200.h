@@ -141,6 +141,41 @@ int fc_update(fc_handle* h, const float* new_pos, int time_step, const float* pr
 int fc_update_lazy(fc_handle* h, const float* new_pos, int time_step, const float* prob_st_0, const float* normalizer,
                    float* base_lp_t, int64_t A, int64_t S, void* stream);
 
+/* ---- consumers immediately after the hot path -------------------------------------------- */
+
+/* Replaces: TP_visualizer.prob_to_grid + griddata_on_cluster (src/visualization/TP_visualizer.py:118-144, 220-251) and the
+ * interp2d ground-truth look-up (:165-179) by DIRECT evaluation of the analytic per-step density on the caller's METRIC
+ * lattice, conditioned on a prefix trajectory (teacher forcing with the ground truth, or the ML prediction):
+ *   out[a, g, t] = p_t(grid_xy[g] | cond_traj[a, :t])   (as_prob != 0)   or its log   (as_prob == 0)
+ * The change of variables is fused into the density kernel: the query of agent a at step t is
+ *   z = (grid_xy[g] - origin[a, t]) * inv_scale[a]      (standardised state of that agent / step)
+ * and log_jac[a] (= -log(std_x std_y dt^2) for 'state_v') is added before the optional exp; see INTEGRATION.md for how
+ * origin / inv_scale / log_jac follow from TP_metrics.unstandardize / output_to_trajectories (TP_metrics.py:68-112).
+ * base_pos (A,2), cond (A,T,C0), cond_traj (A,T,2) standardised, grid_xy (G,2), origin (A,T,2), inv_scale (A,2),
+ * log_jac (A)|NULL, eps (A*G, E)|NULL.  out strides as in fc_grid_log_prob. */
+int fc_grid_density_maps(fc_handle* h, const float* base_pos, const float* cond, const float* cond_traj,
+                         const float* grid_xy, const float* origin, const float* inv_scale, const float* log_jac,
+                         const float* eps, uint64_t seed, int as_prob, float* out, int64_t out_agent_stride,
+                         int64_t out_point_stride, int64_t out_step_stride, int64_t A, int64_t G, int precision, void* stream);
+
+/* Replaces: TP_metrics.unstandardize + output_to_trajectories (src/metrics/TP_metrics.py:68-112) for one tensor:
+ * state_st (A,S,Tk,ncol) standardised state (+ log p when ncol == 3) -> out (same shape): metric positions (+ p = exp(log p)).
+ *   state_mode 0 ('state_p'): pos = st * std + offset[a];  1 ('state_v'): pos = cumsum_t(st * std) * dt[a] + offset[a].
+ * offset (A,2) = obs[:, -1, :2] for key k = 0, the metric ground truth gt[:, k-1, :2] for an update key k > 0; dt (A)|NULL
+ * (= 1); std0 / std1 = the dataset's standardisation scale.  ("pred_st", 0) (B,T,2) is the S = 1, ncol = 2 case. */
+int fc_to_trajectories(fc_handle* h, const float* state_st, const float* offset, const float* dt, float std0, float std1,
+                       int state_mode, float* out, int64_t A, int64_t S, int Tk, int ncol, void* stream);
+
+/* Replaces: the best-of-N ADE/FDE loop of src/main.py:162-180 (N_TRIAL predict calls + deepcopies) and
+ * TP_metrics.__call__ / evaluate_helper (src/metrics/TP_metrics.py:34-46, 163-191) for one batch: cand_st (A,N,T,2) are the
+ * N standardised candidates per agent (one sampler launch with S = N), gt (A,T,2) the METRIC ground truth, last_obs (A,2),
+ * dt (A)|NULL, fallback_st (A,2)|NULL replaces NaN coordinates (fastpredNF.py:131-136).
+ * -> ade_min (A) = min_n mean_t |pred_n - gt|, fde_min (A) = min_n |pred_n[T-1] - gt[T-1]| (independent minima, as the
+ * reference's stack + min), ade_arg / fde_arg (A) int32 | NULL = the winning candidates. */
+int fc_best_of_n(fc_handle* h, const float* cand_st, const float* gt, const float* last_obs, const float* dt,
+                 const float* fallback_st, float std0, float std1, int state_mode, float* ade_min, float* fde_min,
+                 int32_t* ade_arg, int32_t* fde_arg, int64_t A, int64_t N, int T, void* stream);
+
 /* Diagnostic: D[128 x N] = A[128 x K] * B[N x K]^T on the tcgen05 tensor cores (bf16 operands, fp32
  * accumulate) through the same descriptor / TMEM / mbarrier helpers the fused kernel uses.  HOST pointers,
  * row-major fp32; N multiple of 16 in [16,256], K in [1,256].  mode 0: bf16, A and B tiles in shared memory;

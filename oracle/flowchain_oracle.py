@@ -388,3 +388,68 @@ def log_prob_importance(p, base_pos, x, cond, eps_k, dtype=np.float32):
     vals = np.stack([log_prob(p, base_pos, x, cond, e, dtype) for e in eps_k])
     m = vals.max(axis=0)
     return m + np.log(np.exp(vals - m).sum(axis=0)) - np.log(vals.dtype.type(len(eps_k)))
+
+
+# ----------------------------------------------------------------------------------------------
+# consumers right after the hot path
+# ----------------------------------------------------------------------------------------------
+
+def to_trajectories(state_st, offset, dt, std, state_mode, dtype=np.float32):
+    """TP_metrics.unstandardize + output_to_trajectories (src/metrics/TP_metrics.py:68-112) for one tensor
+    state_st (A,S,Tk,ncol), ncol = 2 (standardised state) or 3 (+ log p): positions x std, then 'state_v' (mode 1):
+    cumsum over the step axis * dt + offset, 'state_p' (mode 0): + offset; the last column becomes exp(log p).
+    offset (A,2) = obs[:, -1, :2] for key 0, metric gt[:, k-1, :2] for an update key k; dt (A) (batched = vmap of the
+    reference's batch-size-1 broadcasting)."""
+    x = np.array(state_st, dtype=dtype, copy=True)
+    std = np.asarray(std, dtype=dtype)
+    offset = np.asarray(offset, dtype=dtype)
+    pos = x[..., :2] * std
+    if state_mode == 1:
+        pos = np.cumsum(pos, axis=2, dtype=dtype) * np.asarray(dt, dtype=dtype)[:, None, None, None] + offset[:, None, None, :]
+    else:
+        pos = pos + offset[:, None, None, :]
+    x[..., :2] = pos
+    if x.shape[-1] == 3:
+        x[..., 2] = np.exp(x[..., 2])
+    return x
+
+
+def best_of_n(cand_st, gt, last_obs, dt, fallback_st, std, state_mode, dtype=np.float32):
+    """The ADE/FDE best-of-N evaluation of src/main.py:162-180 for one batch: cand_st (A,N,T,2) standardised candidates
+    (N = TEST.N_TRIAL predictions), NaN coordinates replaced by fallback_st (fastpredNF.py:131-136), un-standardised and
+    integrated (TP_metrics.py:68-112), then displacement_error / final_displacement_error per candidate and the minimum
+    over candidates per agent (TP_metrics.py:34-46, 163-191: stack over trials, min, the caller sums over agents).
+    gt (A,T,2) metric positions.  Returns ade_min (A), fde_min (A), ade_arg (A), fde_arg (A)."""
+    c = np.array(cand_st, dtype=dtype, copy=True)
+    if fallback_st is not None:
+        fb = np.broadcast_to(np.asarray(fallback_st, dtype=dtype)[:, None, None, :], c.shape)
+        c = np.where(np.isnan(c), fb, c)
+    pos = to_trajectories(c, last_obs, dt, std, state_mode, dtype)
+    err = np.linalg.norm(pos - np.asarray(gt, dtype=dtype)[:, None], axis=-1)       # (A, N, T)
+    ade = err.mean(axis=-1)
+    fde = err[..., -1]
+    return ade.min(axis=1), fde.min(axis=1), ade.argmin(axis=1), fde.argmin(axis=1)
+
+
+def density_maps_metric(p, base_pos, cond, cond_traj, grid_xy, origin, inv_scale, log_jac, eps, dtype=np.float32, as_prob=True):
+    """What replaces TP_visualizer.prob_to_grid (src/visualization/TP_visualizer.py:118-179) for FlowChain: the analytic
+    per-step density (a13-ii, prefix = cond_traj) evaluated on a METRIC lattice grid_xy (G,2).  Agent a at step t maps
+    the lattice into its standardised state space with z = (X - origin[a,t]) * inv_scale[a] (the inverse of
+    TP_metrics.unstandardize / output_to_trajectories, TP_metrics.py:68-112) and the density picks up the Jacobian
+    exp(log_jac[a]).  Returns (A,G,T): p, or log p with as_prob=False."""
+    p = cast_params(p, dtype)
+    base_pos, cond, cond_traj, grid_xy, origin, inv_scale, log_jac, eps = (
+        np.asarray(a, dtype=dtype) for a in (base_pos, cond, cond_traj, grid_xy, origin, inv_scale, log_jac, eps))
+    spec = Spec(p)
+    A, T = cond.shape[0], cond.shape[1]
+    G = grid_xy.shape[0]
+    off = spec.eps_offsets()
+    out = np.empty((A * G, T), dtype=dtype)
+    for i in range(T):
+        z = ((grid_xy[None] - origin[:, i, None]) * inv_scale[:, None]).reshape(A * G, 2)
+        y_a = np.concatenate([cond[:, i], cond_traj[:, :i].reshape(A, -1)], axis=-1)
+        w, l = cif_forward(p, spec, i, z, np.repeat(y_a, G, axis=0), eps[:, off[i]:off[i + 1]])
+        prev = base_pos if i == 0 else cond_traj[:, i - 1]
+        out[:, i] = np.sum(normal_log_prob(w, np.repeat(prev, G, axis=0), base_std(p, i)), axis=-1) + l
+    out = out.reshape(A, G, T) + log_jac[:, None, None]
+    return np.exp(out) if as_prob else out

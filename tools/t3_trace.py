@@ -5,8 +5,11 @@ import ctypes, os, sys, numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from flowchain_iccv2023_b200 import synth, _lib
 from flowchain_iccv2023_b200.flow import fastpredNF_CIF_separate_cond
-spec = synth.DEFAULT_SPEC
-f = fastpredNF_CIF_separate_cond(2, 3, 64, 2, 16, flow_architecture='realNVP', pred_len=12)
+# pred_len 8 (default ETH otherwise): every layer is <= 64 wide, so a pass is ONE launch of the HTS layout (a 12-step pass
+# is two launches that write the same trace buffer); set T3_TRACE_T=12 to trace the second (80-wide) launch instead
+T_ = int(os.environ.get('T3_TRACE_T', '8'))
+spec = synth.FlowSpec(pred_len=T_)
+f = fastpredNF_CIF_separate_cond(2, 3, 64, 2, 16, flow_architecture='realNVP', pred_len=T_)
 f.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_params(spec, 0).items()})
 f = f.cuda().eval()
 A = 64
