@@ -602,7 +602,8 @@ static int update_impl(fc_handle* h, const float* new_pos, int t, const float* p
     if (smem > 48 * 1024) FC_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(kUpdCluster, (unsigned)A, 1);
-    cfg.blockDim = dim3(kUpdThreads, 1, 1);
+    // few agents (the reference's B = 1 case): 8 CTAs are all there is, so give each 1024 threads worth of loads in flight
+    cfg.blockDim = dim3(A * kUpdCluster < 2 * (int64_t)h->num_sms ? kUpdMaxThreads : kUpdThreads, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];

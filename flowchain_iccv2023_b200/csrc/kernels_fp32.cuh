@@ -610,7 +610,7 @@ __global__ void k_base_normalizer(const float* __restrict__ base_lp, float* __re
 //            flight per thread, no partial-sum round trip through HBM, no second pass over the positions -- or (lazy)
 //            just lp'(A, S): 40 KB per agent instead of 1.3 MB, for consumers that add ldjs themselves.
 constexpr int kUpdCluster = 8;
-constexpr int kUpdThreads = 256;
+constexpr int kUpdThreads = 256, kUpdMaxThreads = 1024;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -626,7 +626,7 @@ __device__ __forceinline__ float ld_dsmem_f32(const float* local_ptr, uint32_t r
 
 // chunk = samples per CTA (multiple of 4); dynamic shared memory: chunk floats.  per_magic = ceil(2^40 / per).
 template <bool LAZY>
-__global__ void __launch_bounds__(kUpdThreads)
+__global__ void __launch_bounds__(kUpdMaxThreads)
 k_update(const float* __restrict__ new_pos, int t, int T, const float* __restrict__ prob0, const float* __restrict__ ldjs,
          const float* __restrict__ normalizer, float* __restrict__ out, long long S, int chunk, float sd0, float sd1,
          unsigned long long per_magic) {
@@ -634,12 +634,13 @@ k_update(const float* __restrict__ new_pos, int t, int T, const float* __restric
     __shared__ float red[32];
     __shared__ float my_partial;
     const long long ag = blockIdx.y;
+    const int nthr = (int)blockDim.x;          // 256 when many agents fill the chip, 1024 when a few agents must not crawl
     const uint32_t rank = cluster_ctarank();
     const long long s0 = (long long)rank * chunk;
     const int ns = (int)(S - s0 < (long long)chunk ? (S - s0 > 0 ? S - s0 : 0) : chunk);
     const float np0 = __ldg(new_pos + ag * 2), np1 = __ldg(new_pos + ag * 2 + 1);
     float acc = 0.0f;
-    for (int sl = threadIdx.x; sl < ns; sl += kUpdThreads) {
+    for (int sl = threadIdx.x; sl < ns; sl += nthr) {
         const float* q = prob0 + ((ag * S + s0 + sl) * T + (t - 1)) * 3;        // strided: 8 of every 36 T bytes
         const float px = __ldg(q), py = __ldg(q + 1);
         const float v = expf(normal_lp2(px, py, np0, np1, sd0, sd1));
@@ -654,7 +655,7 @@ k_update(const float* __restrict__ new_pos, int t, int T, const float* __restric
     for (int r = 0; r < kUpdCluster; ++r) total += ld_dsmem_f32(&my_partial, (uint32_t)r);     // rank order: deterministic
     cluster_sync_all();                                       // no CTA may exit (or reuse my_partial) while peers still read it
     const float nz = __ldg(normalizer + ag);
-    for (int sl = threadIdx.x; sl < ns; sl += kUpdThreads) {
+    for (int sl = threadIdx.x; sl < ns; sl += nthr) {
         const float lp = logf(upd_bp[sl] / total * nz);       // same order of operations as fastpredNF.py:154-155
         if (LAZY) out[ag * S + s0 + sl] = lp;
         else upd_bp[sl] = lp;
@@ -667,13 +668,13 @@ k_update(const float* __restrict__ new_pos, int t, int T, const float* __restric
     float* dst = out + (ag * S + s0) * per;
     const int nelem = ns * per, T3 = 3 * T;
     constexpr int U = 8;
-    for (int e0 = threadIdx.x; e0 < nelem; e0 += U * kUpdThreads) {
+    for (int e0 = threadIdx.x; e0 < nelem; e0 += U * nthr) {
         float v[U];
         int sls[U];
         bool isl[U];
 #pragma unroll
         for (int k = 0; k < U; ++k) {
-            const int e = e0 + k * kUpdThreads;
+            const int e = e0 + k * nthr;
             const int ec = e < nelem ? e : nelem - 1;
             const int sl = (int)(((unsigned long long)(unsigned)ec * per_magic) >> 40);     // ec / per
             const int r = ec - sl * per;
@@ -685,7 +686,7 @@ k_update(const float* __restrict__ new_pos, int t, int T, const float* __restric
         }
 #pragma unroll
         for (int k = 0; k < U; ++k) {
-            const int e = e0 + k * kUpdThreads;
+            const int e = e0 + k * nthr;
             if (e < nelem) dst[e] = isl[k] ? upd_bp[sls[k]] + v[k] : v[k];
         }
     }

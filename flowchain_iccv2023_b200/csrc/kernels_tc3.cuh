@@ -16,8 +16,10 @@
 // FC_T3_SPLIT_NETS = 1: inside a tile, column part p (4 warps) runs the hidden-layer epilogues of NET p only, over all
 // columns of its rows -- the s-net (tanh, XU-bound) and t-net (ReLU) chains of a tile advance on different warps instead
 // of taking turns on the same eight.  0: the round-1 schedule (both parts share every epilogue, nets in turn).
+// Measured on B200 (config 2): 50.5 ms with the split vs 49.3 ms without -- the tanh chain alone on four warps is
+// latency-bound, so the default stays 0; kept as a build option.
 #ifndef FC_T3_SPLIT_NETS
-#define FC_T3_SPLIT_NETS 1
+#define FC_T3_SPLIT_NETS 0
 #endif
 
 namespace fc {

@@ -397,7 +397,7 @@ def test_wide_tc_matches_fp32_path_at_scale(wide_flows, case):
         # both kernels only carry rounding noise): the bar is asked where the value is resolved in fp32
         sel = np.abs(a32) < 1e4
         print(f"{case} sequential={seqm}: {sel.mean():.4f} of the lattice has |log p| < 1e4")
-        assert sel.mean() > 0.5 and np.isfinite(a16).all()
+        assert sel.mean() > 0.3 and np.isfinite(a16).all()
         # both sides carry their own rounding (the fp32 chain alone is up to 3e-6|ref| x 12 steps off fp64): bulk at the bar,
         # worst point bounded
         check(f"{case} wide f16x3 vs fp32 kernels (philox, sequential={seqm})", a16[sel], a32[sel].astype(np.float64), "f16x3",
