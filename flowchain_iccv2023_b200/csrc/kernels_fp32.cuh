@@ -640,12 +640,24 @@ k_update(const float* __restrict__ new_pos, int t, int T, const float* __restric
     const int ns = (int)(S - s0 < (long long)chunk ? (S - s0 > 0 ? S - s0 : 0) : chunk);
     const float np0 = __ldg(new_pos + ag * 2), np1 = __ldg(new_pos + ag * 2 + 1);
     float acc = 0.0f;
-    for (int sl = threadIdx.x; sl < ns; sl += nthr) {
-        const float* q = prob0 + ((ag * S + s0 + sl) * T + (t - 1)) * 3;        // strided: 8 of every 36 T bytes
-        const float px = __ldg(q), py = __ldg(q + 1);
-        const float v = expf(normal_lp2(px, py, np0, np1, sd0, sd1));
-        upd_bp[sl] = v;
-        acc += v;
+    // strided gather (8 of every 12 T bytes): 8 independent sample loads in flight per thread before any arithmetic
+    for (int sl0 = threadIdx.x; sl0 < ns; sl0 += 8 * nthr) {
+        float px[8], py[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int sl = sl0 + k * nthr;
+            const float* q = prob0 + ((ag * S + s0 + (sl < ns ? sl : ns - 1)) * T + (t - 1)) * 3;
+            px[k] = __ldg(q); py[k] = __ldg(q + 1);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int sl = sl0 + k * nthr;
+            if (sl < ns) {
+                const float v = expf(normal_lp2(px[k], py[k], np0, np1, sd0, sd1));
+                upd_bp[sl] = v;
+                acc += v;
+            }
+        }
     }
     acc = block_sum(acc, red);
     if (threadIdx.x == 0) my_partial = acc;
