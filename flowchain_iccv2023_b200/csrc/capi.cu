@@ -598,18 +598,18 @@ static int update_impl(fc_handle* h, const float* new_pos, int t, const float* p
     if (smem + 1024 > (size_t)h->smem_optin) return fail(h, "too many samples per agent for the update kernel (%lld)", (long long)S);
     const int per = (T - t) * 3;
     const unsigned long long magic = ((1ull << 40) + per - 1) / per;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kUpdCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.stream = (cudaStream_t)stream;
+    cfg.attrs = attr; cfg.numAttrs = 1;
     auto kern = lazy ? k_update<true> : k_update<false>;
     if (smem > 48 * 1024) FC_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(kUpdCluster, (unsigned)A, 1);
     // few agents (the reference's B = 1 case): 8 CTAs are all there is, so give each 1024 threads worth of loads in flight
     cfg.blockDim = dim3(A * kUpdCluster < 2 * (int64_t)h->num_sms ? kUpdMaxThreads : kUpdThreads, 1, 1);
     cfg.dynamicSmemBytes = smem;
-    cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kUpdCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
     FC_CUDA(h, cudaLaunchKernelEx(&cfg, kern, new_pos, t, T, prob_st_0, ldjs, normalizer, out, (long long)S, (int)chunk,
                                   h->plans[t].std[0], h->plans[t].std[1], magic));
     h->launches += 1;

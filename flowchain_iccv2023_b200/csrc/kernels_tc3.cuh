@@ -190,6 +190,12 @@ __device__ __forceinline__ float epi_layer3(uint32_t acc, uint32_t ohi, uint32_t
     return epi_hidden3<NPASS, ACT, DOT, WRITE, BIAS, HTS>(acc, ohi, olo, bias, wlast, part, W, koff);
 #endif
 }
+// e^x = 2^(x log2 e) on the MUFU (2 ulp; denormal results flush to zero, which only ever multiplies the noise)
+__device__ __forceinline__ float fast_exp(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
 __device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
 __device__ __forceinline__ void lds128u(uint32_t saddr, uint32_t* v) {
     asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(saddr));
@@ -652,12 +658,13 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
                         tmem_wait_ld();
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            if (d0 + i < C) {
-                                const float m = mu[i] + bias_mu[d0 + i], l = ls[i] + bias_ls[d0 + i];
-                                u[i] = clamp_h(fmaf(__expf(l), e[i], m));
-                                p_ls += l;
-                                p_e2 = fmaf(e[i], e[i], p_e2);
-                            }
+                            // branch-free: padded columns (d >= C) have zero weights and biases, so mu = ls = 0 there and
+                            // masking the noise alone gives u = 0, no contribution to either sum
+                            const float m = mu[i] + bias_mu[d0 + i], l = ls[i] + bias_ls[d0 + i];
+                            const float en = d0 + i < C ? e[i] : 0.0f;
+                            u[i] = clamp_h(fmaf(fast_exp(l), en, m));
+                            p_ls += l;
+                            p_e2 = fmaf(en, en, p_e2);
                         }
                     }
                     if (d0 == (C & ~7)) {        // mx = z * mask of the first coupling sits at columns C, C+1
@@ -696,16 +703,14 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
                     }
                     tmem_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if (d0 + i < C) {
-                            const __half2 h2 = *reinterpret_cast<const __half2*>(&uh[i >> 1]), l2 = *reinterpret_cast<const __half2*>(&ul[i >> 1]);
-                            const float2 hf = __half22float2(h2), lf = __half22float2(l2);
-                            const float u = (i & 1) ? hf.y + lf.y : hf.x + lf.x;
-                            const float m = mu[i] + bias_mu[d0 + i], l = ls[i] + bias_ls[d0 + i];
-                            const float df = (u - m) * __expf(-l);
-                            p_q = fmaf(df, df, p_q);
-                            p_ls += l;
-                        }
+                    for (int i = 0; i < 8; ++i) {      // branch-free: padded columns carry mu = ls = 0 and u is masked
+                        const __half2 h2 = *reinterpret_cast<const __half2*>(&uh[i >> 1]), l2 = *reinterpret_cast<const __half2*>(&ul[i >> 1]);
+                        const float2 hf = __half22float2(h2), lf = __half22float2(l2);
+                        const float u = d0 + i < C ? ((i & 1) ? hf.y + lf.y : hf.x + lf.x) : 0.0f;     // columns C, C+1 of the operand hold mx, not u
+                        const float m = mu[i] + bias_mu[d0 + i], l = ls[i] + bias_ls[d0 + i];
+                        const float df = (u - m) * fast_exp(-l);
+                        p_q = fmaf(df, df, p_q);
+                        p_ls += l;
                     }
                 }
                 const float s_ls = row_sum3(x, 0, p_ls), s_q = row_sum3(x, 1, p_q);

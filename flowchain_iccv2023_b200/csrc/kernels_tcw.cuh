@@ -552,13 +552,12 @@ __device__ __forceinline__ void tw_compute(const TwStep* __restrict__ steps, con
                         }
                         tmem_wait_ld();
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            if (d0 + i < C) {
-                                const float mm = mu[i] + __ldg(bias_mu + d0 + i), l = ls[i] + __ldg(bias_ls + d0 + i);
-                                u[i] = clamp_h(fmaf(__expf(l), e[i], mm));
-                                p_ls += l;
-                                p_e2 = fmaf(e[i], e[i], p_e2);
-                            }
+                        for (int i = 0; i < 8; ++i) {      // branch-free, see kernels_tc3.cuh (padded columns: mu = ls = 0)
+                            const float mm = mu[i] + __ldg(bias_mu + d0 + i), l = ls[i] + __ldg(bias_ls + d0 + i);
+                            const float en = d0 + i < C ? e[i] : 0.0f;
+                            u[i] = clamp_h(fmaf(t3::fast_exp(l), en, mm));
+                            p_ls += l;
+                            p_e2 = fmaf(en, en, p_e2);
                         }
                     }
                     if (d0 == (C & ~7)) {        // mx = z * mask of the first coupling sits at columns C, C+1 (C is even)
@@ -588,16 +587,14 @@ __device__ __forceinline__ void tw_compute(const TwStep* __restrict__ steps, con
                     tmem_ld4(tU_lo + (uint32_t)(d0 >> 1), ul);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if (d0 + i < C) {
-                            const __half2 h2 = *reinterpret_cast<const __half2*>(&uh[i >> 1]), l2 = *reinterpret_cast<const __half2*>(&ul[i >> 1]);
-                            const float2 hf = __half22float2(h2), lf = __half22float2(l2);
-                            const float u = (i & 1) ? hf.y + lf.y : hf.x + lf.x;
-                            const float mm = mu[i] + __ldg(bias_mu + d0 + i), l = ls[i] + __ldg(bias_ls + d0 + i);
-                            const float df = (u - mm) * __expf(-l);
-                            p_q = fmaf(df, df, p_q);
-                            p_ls += l;
-                        }
+                    for (int i = 0; i < 8; ++i) {      // branch-free: padded columns carry mu = ls = 0 and u is masked
+                        const __half2 h2 = *reinterpret_cast<const __half2*>(&uh[i >> 1]), l2 = *reinterpret_cast<const __half2*>(&ul[i >> 1]);
+                        const float2 hf = __half22float2(h2), lf = __half22float2(l2);
+                        const float u = d0 + i < C ? ((i & 1) ? hf.y + lf.y : hf.x + lf.x) : 0.0f;     // columns C, C+1 of the operand hold mx, not u
+                        const float mm = mu[i] + __ldg(bias_mu + d0 + i), l = ls[i] + __ldg(bias_ls + d0 + i);
+                        const float df = (u - mm) * t3::fast_exp(-l);
+                        p_q = fmaf(df, df, p_q);
+                        p_ls += l;
                     }
                 }
                 const float s_ls = row_sum_w(x, 0, p_ls), s_q = row_sum_w(x, 1, p_q);

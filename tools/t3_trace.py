@@ -68,3 +68,17 @@ allev.sort()
 if allev:
     t0 = allev[0][0]
     for t, w, g in allev[:150]: print(f"{t - t0:8d}  warp {w:2d}  tag {g:#x}")
+
+# ---- per-phase durations of one epilogue warp (mean cycles between consecutive tags) ----
+names = {0x10: "wait MMA net0", 0x11: "wait MMA net1", 0x12: "epilogue net0", 0x13: "epilogue net1", 0x14: "wait both L3",
+         0x15: "E2/E3 gaussian phase", 0x16: "coupling tail / gather"}
+for w in (0, 8):
+    ev = events(w)
+    acc, cnt = {}, {}
+    for (t0, g0), (t1, g1) in zip(ev, ev[1:]):
+        if t1 < t0: continue
+        acc[g0] = acc.get(g0, 0) + (t1 - t0); cnt[g0] = cnt.get(g0, 0) + 1
+    tot = sum(acc.values())
+    print(f"warp {w}: phase means (cycles) and share of time")
+    for g in sorted(acc):
+        print(f"   {names.get(g, hex(g)):28s} n={cnt[g]:4d}  mean {acc[g] / cnt[g]:8.0f}  share {100 * acc[g] / tot:5.1f} %")
