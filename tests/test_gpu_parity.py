@@ -61,6 +61,27 @@ def T(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
+def sampler_check(what, seq, lp, ldjs, g, atol):
+    """Sampler outputs against the golden fp64 reference: tight bar on resolved samples, relative bound on the tail."""
+    ref_seq, ref_lp, ref_ldj = g["sample_seq_64"], g["sample_log_prob_64"], g["sample_ldjs_64"]
+    resolved = (np.abs(ref_ldj) < 1e3).all(axis=-1, keepdims=True) & np.ones_like(ref_ldj, dtype=bool)     # whole trajectories
+    frac = resolved.mean()
+    own_seq = np.abs(g["sample_seq_32"].astype(np.float64) - ref_seq)
+    err_seq = np.abs(seq - ref_seq)
+    r2 = resolved[..., None] & np.ones_like(ref_seq, dtype=bool)
+    assert np.all(err_seq[r2] <= 2e-5 + 1e-5 * np.abs(ref_seq[r2]) + 3 * own_seq[r2]), (what, err_seq[r2].max())
+    for name, out, ref, ref32 in (("ldjs", ldjs, ref_ldj, g["sample_ldjs_32"]), ("log_prob", lp, ref_lp, g["sample_log_prob_32"])):
+        err = np.abs(out - ref)
+        own = np.abs(ref32.astype(np.float64) - ref)
+        tol = atol + 3e-6 * np.abs(ref) + 3 * own
+        print(f"{what} {name}: resolved {frac:.3f} of samples, max|err| there {err[resolved].max():.3e} (reference fp32's own "
+              f"{own[resolved].max():.3e}), max err/tol {np.max(err[resolved] / tol[resolved]):.3f}; tail max rel "
+              f"{np.max(err[~resolved] / (1 + np.abs(ref[~resolved]))) if (~resolved).any() else 0:.2e}")
+        assert frac > 0.5
+        assert np.all(err[resolved] <= tol[resolved]), (what, name)
+        assert np.all(err[~resolved] <= atol + 1e-4 * np.abs(ref[~resolved]) + 3 * own[~resolved]), (what, name, "tail")
+
+
 def g_t(a):
     return torch.from_numpy(np.ascontiguousarray(a))
 
@@ -110,10 +131,12 @@ def test_sample_and_update_golden(flows, case):
     cd = T(g["cond"][:B])[:, None].expand(-1, S, -1, -1)
     seq, lp, ldjs, base = f.sample_with_log_prob(bp, cd, z0=T(g["z0"]), eps=T(g["eps_sample"]))
     assert seq.shape == (B, S, Tn, 2) and lp.shape == (B, S, Tn) and base.shape == (B, S, 1)
-    # the sampled positions feed back autoregressively; compare to fp64 with a position tolerance
-    np.testing.assert_allclose(seq.cpu().numpy(), g["sample_seq_64"], atol=2e-4, rtol=1e-4)
-    np.testing.assert_allclose(ldjs.cpu().numpy(), g["sample_ldjs_64"], atol=2e-3, rtol=1e-4)
-    np.testing.assert_allclose(lp.cpu().numpy(), g["sample_log_prob_64"], atol=2e-3, rtol=1e-4)
+    # The sampled positions feed back autoregressively and a random-init chain makes some samples diverge (|ldj| up to
+    # 5e7), where every rounding error is amplified -- the reference's own fp32 run is hundreds of nats off its fp64 run
+    # there.  So: (1) on the RESOLVED samples (|ldj| < 1e3 at every step) the 1e-4 + 3e-6|ref| bar, widened only by three
+    # times the reference-fp32's own deviation from fp64 on that value; (2) the diverging tail reported and bounded
+    # relatively.
+    sampler_check("fp32 sampler", seq.cpu().numpy(), lp.cpu().numpy(), ldjs.cpu().numpy(), g, 1e-4)
     assert_close32(base.cpu().numpy(), g["sample_base_64"], "base_lp")
 
     # wrapper: predict (sampler + cache) then the rapid update, against the reference wrapper's outputs
@@ -138,12 +161,14 @@ def test_sample_and_update_golden(flows, case):
         ref = g[f"update_t{t}_32"]
         assert out.shape == ref.shape and dd[("pred_st", t)].shape == (B, Tn - t, 2)
         np.testing.assert_array_equal(out[..., :2], ref[..., :2])
-        fin = np.isfinite(ref[..., -1])
-        # -inf on underflow: must agree except within rounding of the underflow threshold
-        mism = fin != np.isfinite(out[..., -1])
-        assert mism.mean() < 0.02
-        ok = fin & ~mism
-        np.testing.assert_allclose(out[..., -1][ok], ref[..., -1][ok], atol=2e-3, rtol=2e-5)
+        # values: against the fp64 oracle evaluated on the SAME (reference fp32) caches, -inf pattern against the fp32 one
+        with np.errstate(all="ignore"):
+            args_u = (dd[("prob_st", 0)].cpu().numpy(), m.ldjs_tmp.cpu().numpy(), m.base_prob_normalizer_tmp[:, 0].cpu().numpy(),
+                      g["gt_st"][:, t - 1], t)
+            r32 = orc.predict_from_new_obs_batched(p, *args_u, np.float32)
+            r64 = orc.predict_from_new_obs_batched(p, *args_u, np.float64)
+        np.testing.assert_allclose(r32[..., -1][np.isfinite(ref[..., -1])], ref[..., -1][np.isfinite(ref[..., -1])], atol=2e-3, rtol=2e-5)   # oracle == reference wrapper
+        _check_update(out, r32, r64, f"{case} update t={t}")
     with pytest.raises(AssertionError):
         m.predict_from_new_obs(dd, 0)
     with pytest.raises(AssertionError):
