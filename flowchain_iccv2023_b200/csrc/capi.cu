@@ -592,26 +592,41 @@ static int update_impl(fc_handle* h, const float* new_pos, int t, const float* p
     if (A == 0 || S == 0) return 0;
     if (!new_pos || !prob_st_0 || !normalizer || !out || (!lazy && !ldjs)) return fail(h, "null tensor pointer");
     if (A > 65535) return fail(h, "too many agents for one update launch (%lld)", (long long)A);
-    // one cluster of kUpdCluster CTAs per agent; a CTA keeps exp(base_lp') of its samples in shared memory
-    const long long chunk = ((S + kUpdCluster - 1) / kUpdCluster + 3) / 4 * 4;
-    const size_t smem = (size_t)chunk * sizeof(float);
-    if (smem + 1024 > (size_t)h->smem_optin) return fail(h, "too many samples per agent for the update kernel (%lld)", (long long)S);
+    // one cluster of 8 CTAs per agent (16 -- a non-portable cluster size -- while the agents alone cannot fill the chip:
+    // the reference's B = 1 call then spreads over 16 SMs); a CTA keeps exp(base_lp') of its samples in shared memory
     const int per = (T - t) * 3;
     const unsigned long long magic = ((1ull << 40) + per - 1) / per;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kUpdCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cudaLaunchConfig_t cfg{};
-    cfg.stream = (cudaStream_t)stream;
-    cfg.attrs = attr; cfg.numAttrs = 1;
     auto kern = lazy ? k_update<true> : k_update<false>;
-    if (smem > 48 * 1024) FC_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cfg.gridDim = dim3(kUpdCluster, (unsigned)A, 1);
-    // few agents (the reference's B = 1 case): 8 CTAs are all there is, so give each 1024 threads worth of loads in flight
-    cfg.blockDim = dim3(A * kUpdCluster < 2 * (int64_t)h->num_sms ? kUpdMaxThreads : kUpdThreads, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    FC_CUDA(h, cudaLaunchKernelEx(&cfg, kern, new_pos, t, T, prob_st_0, ldjs, normalizer, out, (long long)S, (int)chunk,
-                                  h->plans[t].std[0], h->plans[t].std[1], magic));
+    // whether the 16-CTA cluster can be scheduled is a property of the device: ask once, fall back to the portable 8
+    int csize = A * kUpdCluster * 2 <= (int64_t)h->num_sms ? kUpdClusterBig : kUpdCluster;
+    for (;;) {
+        const long long chunk = ((S + csize - 1) / csize + 3) / 4 * 4;
+        const size_t smem = (size_t)chunk * sizeof(float);
+        if (smem + 1024 > (size_t)h->smem_optin) return fail(h, "too many samples per agent for the update kernel (%lld)", (long long)S);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cudaLaunchConfig_t cfg{};
+        cfg.stream = (cudaStream_t)stream;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        if (smem > 48 * 1024) FC_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (csize > 8) FC_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cfg.gridDim = dim3(csize, (unsigned)A, 1);
+        // few agents (the reference's B = 1 case): the cluster is all there is, so give each CTA 1024 threads worth of loads in flight
+        cfg.blockDim = dim3(A * kUpdCluster < 2 * (int64_t)h->num_sms ? kUpdMaxThreads : kUpdThreads, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        if (csize > 8) {
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess || nclusters < 1) {
+                (void)cudaGetLastError();
+                csize = kUpdCluster;
+                continue;
+            }
+        }
+        FC_CUDA(h, cudaLaunchKernelEx(&cfg, kern, new_pos, t, T, prob_st_0, ldjs, normalizer, out, (long long)S, (int)chunk,
+                                      h->plans[t].std[0], h->plans[t].std[1], magic));
+        break;
+    }
     h->launches += 1;
     FC_CUDA(h, cudaGetLastError());
     return 0;

@@ -609,10 +609,11 @@ __global__ void k_base_normalizer(const float* __restrict__ base_lp, float* __re
 //            prob_st_0[:, :, t:] with the log-prob column replaced by lp'[s] + ldjs[s, t+j] -- 8 independent loads in
 //            flight per thread, no partial-sum round trip through HBM, no second pass over the positions -- or (lazy)
 //            just lp'(A, S): 40 KB per agent instead of 1.3 MB, for consumers that add ldjs themselves.
-constexpr int kUpdCluster = 8;
+constexpr int kUpdCluster = 8, kUpdClusterBig = 16;
 constexpr int kUpdThreads = 256, kUpdMaxThreads = 1024;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -663,8 +664,8 @@ k_update(const float* __restrict__ new_pos, int t, int T, const float* __restric
     if (threadIdx.x == 0) my_partial = acc;
     cluster_sync_all();
     float total = 0.0f;
-#pragma unroll
-    for (int r = 0; r < kUpdCluster; ++r) total += ld_dsmem_f32(&my_partial, (uint32_t)r);     // rank order: deterministic
+    const uint32_t csize = cluster_nctarank();                // 8, or 16 (non-portable size) when only a few agents are in flight
+    for (uint32_t r = 0; r < csize; ++r) total += ld_dsmem_f32(&my_partial, r);     // rank order: deterministic
     cluster_sync_all();                                       // no CTA may exit (or reuse my_partial) while peers still read it
     const float nz = __ldg(normalizer + ag);
     for (int sl = threadIdx.x; sl < ns; sl += nthr) {

@@ -23,19 +23,20 @@ def main():
     f.check_versions = False
     h = f.engine()
     S, T = 10000, spec.pred_len
-    for A in (1, 64, 1000):
+    agents = tuple(int(a) for a in sys.argv[1:]) or (1, 64, 1000)
+    for A in agents:
         inp = synth.make_inputs(spec, A, seed=3)
         bp = torch.from_numpy(inp["base_pos"]).cuda()
         cd = torch.from_numpy(inp["cond"]).cuda()
         # sampler (fills the cache): B agents x S samples, 12 autoregressive CIF steps
         for _ in range(2):
-            seq, lp, ldjs, base = torch.ops.flowchain.sample_with_log_prob(h.id, bp, cd, S, None, None, 7, 0)
+            seq, lp, ldjs, base = torch.ops.flowchain.sample_with_log_prob(h.id, bp, cd, S, None, None, 7, 2 if A > 100 else 0)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 3 if A > 100 else 10
         e0.record()
         for _ in range(reps):
-            seq, lp, ldjs, base = torch.ops.flowchain.sample_with_log_prob(h.id, bp, cd, S, None, None, 7, 0)
+            seq, lp, ldjs, base = torch.ops.flowchain.sample_with_log_prob(h.id, bp, cd, S, None, None, 7, 2 if A > 100 else 0)
         e1.record()
         torch.cuda.synchronize()
         sample_ms = e0.elapsed_time(e1) / reps
