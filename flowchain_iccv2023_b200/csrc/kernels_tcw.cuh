@@ -3,22 +3,26 @@
 // kernel (kernels_tc3.cuh, layers <= 80 wide) refuses.
 //
 // Same arithmetic as the two-tile kernel (split-fp16 operands, tcgen05.mma kind::f16, fp32 accumulate in tensor
-// memory, tc_f16x3.cuh), different resource plan, because a 256-wide layer needs 256 accumulator columns and a
-// [128 x 256] hi+lo operand is 128 KB of shared memory:
+// memory, tc_f16x3.cuh), different resource plan: a 256-wide layer needs 256 accumulator columns, and its hi + lo
+// operand would be 128 KB of shared memory read at the SS-mode cost of 172 cycles per MMA (tools/mb_mma.cu), so
 //   * ONE 128-row tile per CTA, 16 epilogue warps (thread = (row = TMEM lane, one of 4 column parts)) + a service
-//     warpgroup (TMA weight producer, MMA issuer);
-//   * the two nets of a sub-network (s|t, shift|log-scale) run ONE AFTER THE OTHER through a single accumulator
-//     [0, A) and a single hidden-operand buffer in shared memory (SS-mode MMAs; the epilogue of layer l overwrites the
-//     operand layer l consumed, which is safe because its MMAs have completed); the means of a density net are parked
-//     in a stash accumulator [A, A + CP) while the log-scale net runs; the narrow first-layer operands [z|w, y] and
-//     [u, mx] live in tensor memory (TS-mode MMAs) behind the stash;
-//   * a 256 x 256 weight matrix (hi + lo = 256 KB) does not fit next to the operands, so every net-layer's weights
-//     are packed as K-SLABS ([N x ks] hi tile + lo tile, <= 16 KB, each in the canonical K-major layout) that stream
-//     from L2 through a TMA ring; a slab is released by the tcgen05.commit of the MMAs that read it;
+//     warpgroup (TMA weight producer, MMA issuer); the two nets of a sub-network run ONE AFTER THE OTHER;
+//   * tensor memory is two 256-column REGIONS that swap roles every layer: layer l accumulates into region l & 1 and
+//     reads its A operand (TS mode: 11 + N/2 cycles per MMA instead of 44 + N/2) from the other one.  The epilogue
+//     converts an accumulator IN PLACE into the next layer's operand: a thread reads 16 fp32 columns of its row and
+//     writes 8 packed-fp16 hi columns + 8 lo columns back into the same 16 columns, which is exactly the K-step layout
+//     a TS-mode MMA reads (hi at 16 k, lo at 16 k + 8);
+//   * every wide layer is issued as two N-HALVES with their own completion barriers, so the epilogue of the first half
+//     overlaps the MMAs of the second (they touch disjoint columns of the accumulator region and the operand region is
+//     read-only until both halves are done);
+//   * the narrow first-layer operands [z|w, y] and [u, mx] live in shared memory (SS mode, K <= 96), the density means
+//     wait in a shared-memory stash (each thread parks and later re-reads its own chunks) while the log-scale net runs;
+//   * the weights are packed per half as K-SLABS ([N_half x ks] hi + lo tile, <= 16 KB, canonical K-major layout each)
+//     that stream from L2 through a TMA ring; a slab is released by the tcgen05.commit of the MMAs that read it;
 //   * biases / last-row vectors are read by the epilogue warps straight from L2/L1 (warp-uniform float4 loads).
-// One job = one net-layer.  Protocol: the compute warps arrive on `opnd` once before every job (operand written,
-// accumulator drained); the issuer waits for it, issues the job's MMAs slab by slab and commits `mma_done`; the
-// compute warps wait for `mma_done` before every epilogue.
+// One job = one net-layer.  Protocol: the compute warps arrive on `opnd` once before every job (operand converted,
+// accumulator region drained); the issuer waits for it, issues half 0 then half 1 slab by slab and commits `done[h]`
+// after each; the compute warps wait for `done[0]` / `done[1]` before the respective half of the epilogue.
 #pragma once
 #include "kernels_tc3.cuh"
 
@@ -28,9 +32,10 @@ constexpr int kTwMaxJobs = 12 + 2 * (kMaxHidden + 1) * kMaxBlocks;
 constexpr int kTwThreads = 16 * 32 + 128;       // 16 compute warps + a service warpgroup (producer, issuer, 2 idle)
 constexpr int kTwComputeRegs = 104, kTwServiceRegs = 56;
 constexpr int kTwHeader = 8192;                 // barriers, step table, row-partial buffers
-constexpr int kTwStepOff = 256, kTwPartOff = 3072;
+constexpr int kTwStepOff = 256, kTwPartOff = 3584;
 constexpr int kTwSlotBytes = 16384;
 constexpr int kTwMaxSlots = 8;
+constexpr uint32_t kTwRegion = 256;             // tensor-memory columns of one region
 
 struct TwStep {
     int32_t C, c, Kin, Ku, Wd, CPd, Hc;
@@ -40,32 +45,35 @@ struct TwStep {
     float bn_iscale[kMaxBlocks][2], bn_ishift[kMaxBlocks][2];
     float std[2];
     // jobs in forward order: [r density: net 0 L1 L2 L3, net 1 L1 L2 L3][block b: s-net L0..Ln, t-net L0..Ln] x n_blocks[q density]
-    uint32_t job_img[kTwMaxJobs];      // byte offset / 16 of the job's first slab in the image
+    uint32_t job_img[kTwMaxJobs];      // byte offset / 16 of the job's first slab (half 0, then half 1) in the image
     uint32_t job_tail[kTwMaxJobs];     // float offset of the job's fp32 tail (bias[N] (+ last-row vector[N], its bias))
-    uint16_t job_kp[kTwMaxJobs], job_n[kTwMaxJobs], job_ks[kTwMaxJobs];   // K (padded), N (padded), slab width
-    uint8_t job_src[kTwMaxJobs];       // A operand: 0 = IN (tensor memory), 1 = U (tensor memory), 2 = hidden (shared memory)
-    uint8_t job_dst[kTwMaxJobs];       // accumulator: 0 = [0, N), 1 = stash [A, A + N)
+    uint16_t job_kp[kTwMaxJobs], job_n[kTwMaxJobs];      // K (padded), N (padded)
+    uint16_t job_n0[kTwMaxJobs];       // N of the first half (multiple of 16); the second half has N - n0 (0: one half only)
+    uint16_t job_ksplit[kTwMaxJobs];   // K columns of the A operand that are ready after `opnd[0]` (the producing layer's first half); 0: wait for all
+    uint8_t job_src[kTwMaxJobs];       // A operand: 0 = IN (shared memory), 1 = U (shared memory), 2 = the other tensor-memory region
+    uint8_t job_reg[kTwMaxJobs];       // accumulator region of the job (layer index & 1)
 };
 static_assert(sizeof(TwStep) <= kTwPartOff - kTwStepOff, "TwStep must fit the header");
 
 struct TwDims {
     int32_t supported;
     int32_t T, C0;
-    int32_t Wmax;                          // widest hidden operand: stride of the shared-memory operand tiles
-    int32_t stash_col;                     // A = widest accumulator
-    int32_t in_hi, in_lo, u_hi, u_lo;      // tensor-memory columns of the first-layer operands
+    int32_t Kmax;                          // widest first-layer operand: [128 x Kmax] fp16 tiles in shared memory
+    int32_t CPmax;                         // widest density output: stash of [CPmax/8][128][8] floats
     int32_t slot_bytes, nslots;
     int32_t step_lo, step_hi;              // per-step mode: steps covered; chain mode: result indices
     int32_t seq;                           // 0 per-step density, 1 chain, 2 sampler
     int32_t klo, jlo;
 };
 
-// slab width of a job: as many 16-wide K steps as fit a ring slot
+// slab width of a half-job: as many 16-wide K steps as fit a ring slot
 inline int tw_slab_k(int N, int Kp, int parts, int slot_bytes) {
     int ks = (slot_bytes / (N * 2 * parts)) & ~15;
     if (ks < 16) ks = 16;
     return ks < Kp ? ks : Kp;
 }
+// first half of an N-wide layer: layers of 128 columns and more are issued as two halves
+inline int tw_first_half(int N) { return N >= 128 ? (N / 32) * 16 : N; }
 
 // Packs the wide image.  dm.supported = 0 for shapes this kernel does not cover.
 inline void tcw_pack(const fc_model_desc& d, const std::vector<StepPlan>& plans, const std::vector<TcStepSrc>& src, int npass,
@@ -76,13 +84,10 @@ inline void tcw_pack(const fc_model_desc& d, const std::vector<StepPlan>& plans,
     const int T = d.pred_len, H = d.hidden_size, parts = npass == 3 ? 2 : 1;
     const int Cmax = d.cond_size + (T - 1) * 2, cmax = Cmax + 2;
     const int Wd_max = pad16i(2 * cmax), Kmax = pad16i(cmax), CPmax = pad16i(Cmax);
-    if (H % 16 != 0 || H > 256 || (d.cond_size & 1) || Wd_max > 256) return;
-    const int A = Wd_max > H ? Wd_max : H;
-    if (A + CPmax + 2 * Kmax > 512) return;                       // tensor-memory columns
-    dm.T = T; dm.C0 = d.cond_size; dm.Wmax = A; dm.stash_col = A;
-    dm.in_hi = A + CPmax; dm.in_lo = dm.in_hi + Kmax / 2; dm.u_hi = dm.in_hi + Kmax; dm.u_lo = dm.u_hi + Kmax / 2;
+    if (H % 16 != 0 || H > 256 || (d.cond_size & 1) || Wd_max > 256) return;      // two 256-column regions
+    dm.T = T; dm.C0 = d.cond_size; dm.Kmax = Kmax; dm.CPmax = CPmax;
     dm.slot_bytes = kTwSlotBytes;
-    const long long ring = (long long)smem_optin - kTwHeader - (long long)2 * 128 * A * 2;
+    const long long ring = (long long)smem_optin - kTwHeader - (long long)4 * 128 * Kmax * 2 - (long long)128 * CPmax * 4;
     dm.nslots = (int)(ring / dm.slot_bytes);
     if (dm.nslots > kTwMaxSlots) dm.nslots = kTwMaxSlots;
     if (dm.nslots < 2) return;                                    // shared memory
@@ -106,21 +111,27 @@ inline void tcw_pack(const fc_model_desc& d, const std::vector<StepPlan>& plans,
         }
         ts.std[0] = sp.std[0]; ts.std[1] = sp.std[1];
         int nj = 0;
-        // one job: W [rows x K] (row-major, nn.Linear.weight) -> K-slabs of canonical K-major tiles; tail = bias (+ extra)
-        auto job = [&](const float* W, const float* bias, int rows, int K, int N, int Kp, int src_, int dst_, const float* extra, int n_extra) {
+        // one job: W [rows x K] (row-major, nn.Linear.weight) -> per N-half, K-slabs of canonical K-major tiles; tail = bias (+ extra)
+        auto job = [&](const float* W, const float* bias, int rows, int K, int N, int Kp, int src_, int layer, const float* extra, int n_extra) {
             while (img.size() % 128) img.push_back(0);
             ts.job_img[nj] = (uint32_t)(img.size() / 16);
-            const int Ks = tw_slab_k(N, Kp, parts, dm.slot_bytes);
-            for (int k0 = 0; k0 < Kp; k0 += Ks) {
-                const int ksl = Ks < Kp - k0 ? Ks : Kp - k0;
-                const int kv = K - k0 < 0 ? 0 : (K - k0 < ksl ? K - k0 : ksl);      // valid (unpadded) columns of this slab
-                sub.assign((size_t)rows * (kv > 0 ? kv : 1), 0.0f);
-                for (int r = 0; r < rows; ++r)
-                    for (int k = 0; k < kv; ++k) sub[(size_t)r * kv + k] = W[(size_t)r * K + k0 + k];
-                for (int part = 0; part < parts; ++part) {
-                    const size_t o = img.size();
-                    img.resize(o + (size_t)N * ksl * 2);
-                    pack_kmajor_f16(img.data() + o, sub.data(), rows, kv, N, ksl, part);
+            const int n0 = tw_first_half(N);
+            for (int half = 0; half < 2; ++half) {
+                const int r0 = half == 0 ? 0 : n0, Nh = half == 0 ? n0 : N - n0;
+                if (Nh == 0) continue;
+                const int Ks = tw_slab_k(Nh, Kp, parts, dm.slot_bytes);
+                const int rv = rows - r0 < 0 ? 0 : (rows - r0 < Nh ? rows - r0 : Nh);       // valid (unpadded) rows of this half
+                for (int k0 = 0; k0 < Kp; k0 += Ks) {
+                    const int ksl = Ks < Kp - k0 ? Ks : Kp - k0;
+                    const int kv = K - k0 < 0 ? 0 : (K - k0 < ksl ? K - k0 : ksl);  // valid (unpadded) columns of this slab
+                    sub.assign((size_t)(rv > 0 ? rv : 1) * (kv > 0 ? kv : 1), 0.0f);
+                    for (int r = 0; r < rv; ++r)
+                        for (int k = 0; k < kv; ++k) sub[(size_t)r * kv + k] = W[(size_t)(r0 + r) * K + k0 + k];
+                    for (int part = 0; part < parts; ++part) {
+                        const size_t o = img.size();
+                        img.resize(o + (size_t)Nh * ksl * 2);
+                        pack_kmajor_f16(img.data() + o, sub.data(), rv, kv, Nh, ksl, part);
+                    }
                 }
             }
             while (tails.size() % 4) tails.push_back(0.0f);
@@ -129,16 +140,18 @@ inline void tcw_pack(const fc_model_desc& d, const std::vector<StepPlan>& plans,
             tails.resize(o + (size_t)N + n_extra, 0.0f);
             memcpy(tails.data() + o, bias, (size_t)rows * 4);
             if (n_extra) memcpy(tails.data() + o + N, extra, (size_t)n_extra * 4);
-            ts.job_kp[nj] = (uint16_t)Kp; ts.job_n[nj] = (uint16_t)N; ts.job_ks[nj] = (uint16_t)Ks;
-            ts.job_src[nj] = (uint8_t)src_; ts.job_dst[nj] = (uint8_t)dst_;
+            ts.job_kp[nj] = (uint16_t)Kp; ts.job_n[nj] = (uint16_t)N; ts.job_n0[nj] = (uint16_t)n0;
+            ts.job_src[nj] = (uint8_t)src_; ts.job_reg[nj] = (uint8_t)(layer & 1);
+            // a tensor-memory operand produced by a two-half layer becomes available half by half
+            ts.job_ksplit[nj] = (uint16_t)((src_ == 2 && nj > 0 && ts.job_n0[nj - 1] < ts.job_n[nj - 1] && ts.job_n[nj - 1] == Kp) ? ts.job_n0[nj - 1] : 0);
             ++nj;
         };
         auto dens = [&](int which) {
             const int h2 = 2 * c;
             for (int net = 0; net < 2; ++net) {
                 job(s.dens_W[which][net][0], s.dens_b[which][net][0], h2, c, ts.Wd, ts.Kin, 0, 0, nullptr, 0);
-                job(s.dens_W[which][net][1], s.dens_b[which][net][1], h2, h2, ts.Wd, ts.Wd, 2, 0, nullptr, 0);
-                job(s.dens_W[which][net][2], s.dens_b[which][net][2], C, h2, ts.CPd, ts.Wd, 2, net == 0 ? 1 : 0, nullptr, 0);
+                job(s.dens_W[which][net][1], s.dens_b[which][net][1], h2, h2, ts.Wd, ts.Wd, 2, 1, nullptr, 0);
+                job(s.dens_W[which][net][2], s.dens_b[which][net][2], C, h2, ts.CPd, ts.Wd, 2, 2, nullptr, 0);
             }
         };
         dens(0);
@@ -162,7 +175,7 @@ inline void tcw_pack(const fc_model_desc& d, const std::vector<StepPlan>& plans,
                         for (float& v : bs) v *= kTanhPrescale;
                         Wl = Ws.data(); bl = bs.data();
                     }
-                    job(Wl, bl, H, Kl, H, l == 0 ? ts.Ku : H, l == 0 ? 1 : 2, 0, extra.empty() ? nullptr : extra.data(), (int)extra.size());
+                    job(Wl, bl, H, Kl, H, l == 0 ? ts.Ku : H, l == 0 ? 1 : 2, l, extra.empty() ? nullptr : extra.data(), (int)extra.size());
                 }
         }
         dens(1);
@@ -173,7 +186,9 @@ inline void tcw_pack(const fc_model_desc& d, const std::vector<StepPlan>& plans,
     dm.supported = 1;
 }
 
-inline size_t tcw_smem_bytes(const TwDims& dm) { return (size_t)kTwHeader + (size_t)2 * 128 * dm.Wmax * 2 + (size_t)dm.nslots * dm.slot_bytes; }
+inline size_t tcw_smem_bytes(const TwDims& dm) {
+    return (size_t)kTwHeader + (size_t)4 * 128 * dm.Kmax * 2 + (size_t)128 * dm.CPmax * 4 + (size_t)dm.nslots * dm.slot_bytes;
+}
 
 namespace tw {
 using namespace tc;
@@ -181,7 +196,7 @@ using namespace t2;
 
 struct BarsW {
     uint64_t full[kTwMaxSlots], empty[kTwMaxSlots];
-    uint64_t mma_done, opnd;
+    uint64_t done[2], opnd[2];
 };
 static_assert(sizeof(BarsW) <= 240, "barrier block");
 
@@ -189,17 +204,18 @@ struct SmemW {
     BarsW* bars;
     TwStep* cur;
     float* part_buf;          // [2 slots][4 parts][128 rows]
-    uint8_t *hbuf, *slots;
-    uint32_t h_stride;
+    uint8_t *inu, *stash, *slots;
+    uint32_t inu_stride;      // one [128 x Kmax] fp16 tile
 };
 __device__ __forceinline__ SmemW tw_smem(uint8_t* smem, const TwDims& dm) {
     SmemW m;
     m.bars = reinterpret_cast<BarsW*>(smem);
     m.cur = reinterpret_cast<TwStep*>(smem + kTwStepOff);
     m.part_buf = reinterpret_cast<float*>(smem + kTwPartOff);
-    m.h_stride = (uint32_t)(128 * dm.Wmax * 2);
-    m.hbuf = smem + kTwHeader;                     // [hi, lo] x [128 x Wmax] fp16
-    m.slots = m.hbuf + (size_t)2 * m.h_stride;
+    m.inu_stride = (uint32_t)(128 * dm.Kmax * 2);
+    m.inu = smem + kTwHeader;                       // [IN hi, IN lo, U hi, U lo] x [128 x Kmax] fp16, canonical K-major
+    m.stash = m.inu + (size_t)4 * m.inu_stride;     // [CPmax / 8][128 rows][8] fp32: density means
+    m.slots = m.stash + (size_t)128 * dm.CPmax * 4;
     return m;
 }
 __device__ __forceinline__ void tw_load_step(const TwStep* steps, int step, TwStep* cur, int tid) {
@@ -245,7 +261,7 @@ __device__ __forceinline__ void tw_idle(const TwStep* __restrict__ steps, const 
     TW_ITEM_END
 }
 
-// ===== weight producer (one warp): streams the K-slabs of every job of the step through the ring =====
+// ===== weight producer (one warp): streams the K-slabs of every half-job of the step through the ring =====
 template <int NPASS>
 __device__ __forceinline__ void tw_producer(const TwStep* __restrict__ steps, const uint8_t* __restrict__ img, const TwDims& dm,
                                             long long tiles_per_step, long long total_items, uint8_t* smem) {
@@ -259,86 +275,134 @@ __device__ __forceinline__ void tw_producer(const TwStep* __restrict__ steps, co
     TW_STEP_BEGIN(dm.seq)
         for (int ji = 0; ji < ts.njobs; ++ji) {
             const int pj = tw_img_job(ts, ji, dm.seq == 2);
-            const int N = ts.job_n[pj], Kp = ts.job_kp[pj], Ks = ts.job_ks[pj];
+            const int N = ts.job_n[pj], n0 = ts.job_n0[pj], Kp = ts.job_kp[pj];
             const uint8_t* srcp = img + (size_t)ts.job_img[pj] * 16;
-            for (int k0 = 0; k0 < Kp; k0 += Ks) {
-                const int ksl = Ks < Kp - k0 ? Ks : Kp - k0;
-                const uint32_t bytes = (uint32_t)(N * ksl * 2 * PARTS);
-                if (lane == 0) {
-                    mbar_wait(&bars->empty[slot], phase ^ 1u);
-                    mbar_expect_tx(&bars->full[slot], bytes);
-                    bulk_load(m.slots + (size_t)slot * dm.slot_bytes, srcp, bytes, &bars->full[slot]);
+            for (int half = 0; half < 2; ++half) {
+                const int Nh = half == 0 ? n0 : N - n0;
+                if (Nh == 0) break;
+                int Ks = (dm.slot_bytes / (Nh * 2 * PARTS)) & ~15;
+                Ks = Ks < 16 ? 16 : Ks;
+                for (int k0 = 0; k0 < Kp; k0 += Ks) {
+                    const int ksl = Ks < Kp - k0 ? Ks : Kp - k0;
+                    const uint32_t bytes = (uint32_t)(Nh * ksl * 2 * PARTS);
+                    if (lane == 0) {
+                        mbar_wait(&bars->empty[slot], phase ^ 1u);
+#ifdef FC_TW_NOWEIGHTS      /* timing experiment only: no weight traffic, the MMAs read whatever is in the slot */
+                        mbar_arrive(&bars->full[slot]);
+#else
+                        mbar_expect_tx(&bars->full[slot], bytes);
+                        bulk_load(m.slots + (size_t)slot * dm.slot_bytes, srcp, bytes, &bars->full[slot]);
+#endif
+                    }
+                    __syncwarp();
+                    srcp += bytes;
+                    if (++slot == dm.nslots) { slot = 0; phase ^= 1u; }
                 }
-                __syncwarp();
-                srcp += bytes;
-                if (++slot == dm.nslots) { slot = 0; phase ^= 1u; }
             }
         }
     TW_STEP_END
     TW_ITEM_END
 }
 
-// ===== MMA issuer (one warp): job by job, slab by slab =====
+// MMAs of one K-slab of a half-job, straight line.  TS: A from the other tensor-memory region in the in-place layout
+// (K-step ks: hi at 16 ks, lo at 16 ks + 8); otherwise A from the shared-memory IN / U tiles.
+template <int NPASS, int NK, bool TS>
+__device__ __forceinline__ void issue_slab(uint32_t acc, uint32_t ta, uint64_t ahi, uint64_t alo, uint64_t dhi, uint64_t dlo, uint32_t idesc,
+                                           uint32_t acc0) {
+#pragma unroll
+    for (int ks = 0; ks < NK; ++ks) {
+        if (TS) umma_ts(acc, ta + ks * 16, dhi + (uint64_t)(ks * 16), idesc, ks > 0 ? 1u : acc0);
+        else umma_bf16(acc, ahi + (uint64_t)(ks * 16), dhi + (uint64_t)(ks * 16), idesc, ks > 0 ? 1u : acc0);
+    }
+    if (NPASS == 3) {
+#pragma unroll
+        for (int ks = 0; ks < NK; ++ks) {
+            if (TS) umma_ts(acc, ta + ks * 16 + 8, dhi + (uint64_t)(ks * 16), idesc, 1u);
+            else umma_bf16(acc, alo + (uint64_t)(ks * 16), dhi + (uint64_t)(ks * 16), idesc, 1u);
+        }
+#pragma unroll
+        for (int ks = 0; ks < NK; ++ks) {
+            if (TS) umma_ts(acc, ta + ks * 16, dlo + (uint64_t)(ks * 16), idesc, 1u);
+            else umma_bf16(acc, ahi + (uint64_t)(ks * 16), dlo + (uint64_t)(ks * 16), idesc, 1u);
+        }
+    }
+}
+template <int NPASS, bool TS>
+__device__ __forceinline__ void issue_slab_n(int nk, uint32_t acc, uint32_t ta, uint64_t ahi, uint64_t alo, uint64_t dhi, uint64_t dlo,
+                                             uint32_t idesc, uint32_t acc0) {
+    switch (nk) {
+        case 1: issue_slab<NPASS, 1, TS>(acc, ta, ahi, alo, dhi, dlo, idesc, acc0); break;
+        case 2: issue_slab<NPASS, 2, TS>(acc, ta, ahi, alo, dhi, dlo, idesc, acc0); break;
+        case 3: issue_slab<NPASS, 3, TS>(acc, ta, ahi, alo, dhi, dlo, idesc, acc0); break;
+        case 4: issue_slab<NPASS, 4, TS>(acc, ta, ahi, alo, dhi, dlo, idesc, acc0); break;
+        default:        // wider slabs (narrow layers): two straight-line groups at a time
+            for (int k = 0; k < nk; k += 2) {
+                if (k + 1 < nk) issue_slab<NPASS, 2, TS>(acc, ta + k * 16, ahi + (uint64_t)(k * 16), alo + (uint64_t)(k * 16), dhi + (uint64_t)(k * 16), dlo + (uint64_t)(k * 16), idesc, k ? 1u : acc0);
+                else issue_slab<NPASS, 1, TS>(acc, ta + k * 16, ahi + (uint64_t)(k * 16), alo + (uint64_t)(k * 16), dhi + (uint64_t)(k * 16), dlo + (uint64_t)(k * 16), idesc, k ? 1u : acc0);
+            }
+            break;
+    }
+}
+
+// ===== MMA issuer (one warp): job by job, half by half, slab by slab =====
 template <int NPASS>
 __device__ __forceinline__ void tw_issuer(const TwStep* __restrict__ steps, const TwDims& dm, long long tiles_per_step, long long total_items,
                                           uint8_t* smem, uint32_t tmem_base) {
     const SmemW m = tw_smem(smem, dm);
     BarsW* bars = m.bars;
+    constexpr int PARTS = NPASS == 3 ? 2 : 1;
     int slot = 0;
     uint32_t phase = 0, opnd_cnt = 0;
-    const uint32_t sa_hi = smem_u32(m.hbuf), sa_lo = sa_hi + m.h_stride;
     TW_ITEM_BEGIN(dm.seq)
     TW_STEP_BEGIN(dm.seq)
 #pragma unroll 1
         for (int ji = 0; ji < ts.njobs; ++ji) {
-            const int Kp = ts.job_kp[ji], N = ts.job_n[ji], Ks = ts.job_ks[ji], src = ts.job_src[ji];
-            const uint32_t acc = tmem_base + (ts.job_dst[ji] ? (uint32_t)dm.stash_col : 0u);
-            const uint32_t idesc = umma_idesc_f16(128, N), sboA = (uint32_t)(Kp >> 3) * 128u;
-            const uint32_t ta_hi = tmem_base + (uint32_t)(src == 0 ? dm.in_hi : dm.u_hi), ta_lo = tmem_base + (uint32_t)(src == 0 ? dm.in_lo : dm.u_lo);
-            const uint64_t ahi = umma_desc(sa_hi, 128, sboA), alo = umma_desc(sa_lo, 128, sboA);
+            const int Kp = ts.job_kp[ji], N = ts.job_n[ji], n0 = ts.job_n0[ji], src = ts.job_src[ji], reg = ts.job_reg[ji];
+            const uint32_t sboA = (uint32_t)(Kp >> 3) * 128u;
+            const uint32_t sa = smem_u32(m.inu) + (uint32_t)(src == 1 ? 2 : 0) * m.inu_stride;
+            const uint64_t ahi = umma_desc(sa, 128, sboA), alo = umma_desc(sa + m.inu_stride, 128, sboA);
+            const uint32_t ta = tmem_base + (uint32_t)(1 - reg) * kTwRegion;        // A operand region (src == 2)
             uint32_t leader;
             asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(leader));
-            // operand of this job written, accumulator drained by the previous epilogue
-            mbar_wait(&bars->opnd, opnd_cnt & 1u);
+            // opnd[0]: the accumulator region is drained and the first `ksplit` K columns of the operand are converted (all of
+            // it when ksplit == 0 / shared-memory operands); opnd[1]: the rest.  Starting the K-low slabs under the second
+            // half of the producing layer's epilogue is safe: they read converted columns only and write the region whose
+            // last readers (that layer's MMAs) precede them in the in-order tensor pipe.
+            const int ksplit = ts.job_ksplit[ji];
+            mbar_wait(&bars->opnd[0], opnd_cnt & 1u);
+            bool all_ready = false;
+            if (ksplit == 0) { mbar_wait(&bars->opnd[1], opnd_cnt & 1u); all_ready = true; }
             opnd_cnt++;
             tc_fence_after();
-            uint32_t accum = 0u;
 #pragma unroll 1
-            for (int k0 = 0; k0 < Kp; k0 += Ks) {
-                const int ksl = Ks < Kp - k0 ? Ks : Kp - k0, nk = ksl >> 4, kg0 = k0 >> 4;
-                mbar_wait(&bars->full[slot], phase);
-                tc_fence_after();
-                const uint32_t b_hi = smem_u32(m.slots + (size_t)slot * dm.slot_bytes), sboB = (uint32_t)(ksl >> 3) * 128u;
-                const uint64_t dhi = umma_desc(b_hi, 128, sboB), dlo = umma_desc(b_hi + (uint32_t)(N * ksl * 2), 128, sboB);
-                if (leader) {
-                    // straight-line issue (compile-time operand offsets inside the slab), see t3::issue_job
-                    const uint32_t tah = ta_hi + (uint32_t)(kg0 * 8), tal = ta_lo + (uint32_t)(kg0 * 8);
-                    const uint64_t sah = ahi + (uint64_t)(kg0 * 16), sal = alo + (uint64_t)(kg0 * 16);
-                    if (src < 2) {
-                        switch (nk) {
-                            case 1: t3::issue_job<NPASS, 1, true>(acc, tah, tal, 0, 0, dhi, dlo, idesc, accum); break;
-                            case 2: t3::issue_job<NPASS, 2, true>(acc, tah, tal, 0, 0, dhi, dlo, idesc, accum); break;
-                            case 3: t3::issue_job<NPASS, 3, true>(acc, tah, tal, 0, 0, dhi, dlo, idesc, accum); break;
-                            case 4: t3::issue_job<NPASS, 4, true>(acc, tah, tal, 0, 0, dhi, dlo, idesc, accum); break;
-                            default: t3::issue_job_loop<NPASS, true>(nk, acc, tah, tal, 0, 0, dhi, dlo, idesc, accum); break;
-                        }
-                    } else {
-                        switch (nk) {
-                            case 1: t3::issue_job<NPASS, 1, false>(acc, 0, 0, sah, sal, dhi, dlo, idesc, accum); break;
-                            case 2: t3::issue_job<NPASS, 2, false>(acc, 0, 0, sah, sal, dhi, dlo, idesc, accum); break;
-                            case 3: t3::issue_job<NPASS, 3, false>(acc, 0, 0, sah, sal, dhi, dlo, idesc, accum); break;
-                            case 4: t3::issue_job<NPASS, 4, false>(acc, 0, 0, sah, sal, dhi, dlo, idesc, accum); break;
-                            default: t3::issue_job_loop<NPASS, false>(nk, acc, 0, 0, sah, sal, dhi, dlo, idesc, accum); break;
-                        }
+            for (int half = 0; half < 2; ++half) {
+                const int Nh = half == 0 ? n0 : N - n0;
+                if (Nh == 0) break;
+                const uint32_t acc = tmem_base + (uint32_t)reg * kTwRegion + (uint32_t)(half == 0 ? 0 : n0);
+                const uint32_t idesc = umma_idesc_f16(128, Nh);
+                int Ks = (dm.slot_bytes / (Nh * 2 * PARTS)) & ~15;
+                Ks = Ks < 16 ? 16 : Ks;
+                uint32_t accum = 0u;
+#pragma unroll 1
+                for (int k0 = 0; k0 < Kp; k0 += Ks) {
+                    const int ksl = Ks < Kp - k0 ? Ks : Kp - k0, nk = ksl >> 4, kg0 = k0 >> 4;
+                    if (!all_ready && k0 + ksl > ksplit) { mbar_wait(&bars->opnd[1], (opnd_cnt - 1u) & 1u); all_ready = true; tc_fence_after(); }
+                    mbar_wait(&bars->full[slot], phase);
+                    tc_fence_after();
+                    const uint32_t b_hi = smem_u32(m.slots + (size_t)slot * dm.slot_bytes), sboB = (uint32_t)(ksl >> 3) * 128u;
+                    const uint64_t dhi = umma_desc(b_hi, 128, sboB), dlo = umma_desc(b_hi + (uint32_t)(Nh * ksl * 2), 128, sboB);
+                    if (leader) {
+                        if (src == 2) issue_slab_n<NPASS, true>(nk, acc, ta + (uint32_t)(kg0 * 16), 0, 0, dhi, dlo, idesc, accum);
+                        else issue_slab_n<NPASS, false>(nk, acc, 0, ahi + (uint64_t)(kg0 * 16), alo + (uint64_t)(kg0 * 16), dhi, dlo, idesc, accum);
+                        accum = 1u;
+                        umma_commit(&bars->empty[slot]);          // slab consumed -> slot back to the producer
                     }
-                    accum = 1u;
-                    umma_commit(&bars->empty[slot]);          // slab consumed -> slot back to the producer
+                    __syncwarp();
+                    if (++slot == dm.nslots) { slot = 0; phase ^= 1u; }
                 }
+                if (leader) umma_commit(&bars->done[half]);
                 __syncwarp();
-                if (++slot == dm.nslots) { slot = 0; phase ^= 1u; }
             }
-            if (leader) umma_commit(&bars->mma_done);
-            __syncwarp();
         }
     TW_STEP_END
     TW_ITEM_END
@@ -349,24 +413,27 @@ struct XW {
     int row, part, lane;
     uint32_t tb;              // tensor-memory base incl. this warp's lane quadrant
     BarsW* bars;
-    uint32_t mma_cnt;
+    uint32_t cnt0, cnt1;      // phases of done[0] / done[1] consumed so far
     float* part_buf;
-    uint32_t h_hi, h_lo;      // shared addresses of the hidden operand tiles
     const float* tails;
 };
-__device__ __forceinline__ void wait_mma_w(XW& x) {
-    mbar_wait(&x.bars->mma_done, x.mma_cnt & 1u);
-    x.mma_cnt++;
+__device__ __forceinline__ void wait_half(XW& x, int half) {
+    if (half == 0) { mbar_wait(&x.bars->done[0], x.cnt0 & 1u); x.cnt0++; }
+    else { mbar_wait(&x.bars->done[1], x.cnt1 & 1u); x.cnt1++; }
     tc_fence_after();
 }
 // this warp's tensor-memory accesses and shared-memory operand stores are complete -> the next job may be issued
-__device__ __forceinline__ void arrive_w(const XW& x) {
+// which: 0 -> opnd[0] only (first half of a layer converted), 1 -> opnd[1] only, 2 -> both (everything else)
+__device__ __forceinline__ void arrive_w(const XW& x, int which = 2) {
     tmem_wait_ld();
     tmem_wait_st();
     fence_async_smem();
     tc_fence_before();
     __syncwarp();
-    if (x.lane == 0) mbar_arrive(&x.bars->opnd);
+    if (x.lane == 0) {
+        if (which != 1) mbar_arrive(&x.bars->opnd[0]);
+        if (which != 0) mbar_arrive(&x.bars->opnd[1]);
+    }
 }
 __device__ __forceinline__ float row_sum_w(const XW& x, int slot, float v) {      // slot in {0, 1}
     float* p = x.part_buf + slot * 512;
@@ -376,55 +443,73 @@ __device__ __forceinline__ float row_sum_w(const XW& x, int slot, float v) {    
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void tmem_st8u(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                 "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
 
-// 8 accumulator values (+ bias) -> activation -> hi / lo fp16 rows of the next layer's shared-memory operand tile,
-// or (DOT) contracted with the surviving row of the final H -> 2 Linear
-template <int NPASS, int ACT, bool DOT, bool WRITE>
-__device__ __forceinline__ void epi_chunk_w(float* u, int c0, const float4 b0, const float4 b1, const float* __restrict__ wlast, uint32_t ohi, uint32_t olo,
-                                            uint32_t koff, float& dot) {
+// 16 accumulator values of this thread's row (+ bias) -> activation -> IN PLACE the K-step of the next layer's TS operand
+// (8 packed hi columns, 8 packed lo columns), or (DOT) contracted with the surviving row of the final H -> 2 Linear.
+template <int NPASS, int ACT, bool DOT>
+__device__ __forceinline__ void epi_math16(float* u, uint32_t acc, int c0, const float* __restrict__ bias, const float* __restrict__ wlast,
+                                           float& dot) {
+    const float4 b0 = ldg4(bias + c0), b1 = ldg4(bias + c0 + 4), b2 = ldg4(bias + c0 + 8), b3 = ldg4(bias + c0 + 12);
     u[0] += b0.x; u[1] += b0.y; u[2] += b0.z; u[3] += b0.w; u[4] += b1.x; u[5] += b1.y; u[6] += b1.z; u[7] += b1.w;
+    u[8] += b2.x; u[9] += b2.y; u[10] += b2.z; u[11] += b2.w; u[12] += b3.x; u[13] += b3.y; u[14] += b3.z; u[15] += b3.w;
     if (ACT == ACT_T) {
 #pragma unroll
-        for (int q = 0; q < 8; q += 2) {
+        for (int q = 0; q < 16; q += 2) {
             if (NPASS == 3) tanh_acc2(u[q], u[q + 1]);
             else { asm("tanh.approx.f32 %0, %0;" : "+f"(u[q])); asm("tanh.approx.f32 %0, %0;" : "+f"(u[q + 1])); }
         }
     } else if (DOT) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) u[q] = fmaxf(u[q], 0.0f);
+        for (int q = 0; q < 16; ++q) u[q] = fmaxf(u[q], 0.0f);
     }
     if (DOT) {
-        const float4 w0 = ldg4(wlast + c0), w1 = ldg4(wlast + c0 + 4);
-        dot = fmaf(u[0], w0.x, dot); dot = fmaf(u[1], w0.y, dot); dot = fmaf(u[2], w0.z, dot); dot = fmaf(u[3], w0.w, dot);
-        dot = fmaf(u[4], w1.x, dot); dot = fmaf(u[5], w1.y, dot); dot = fmaf(u[6], w1.z, dot); dot = fmaf(u[7], w1.w, dot);
-    }
-    if (WRITE) {
-        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 16; q += 4) {
+            const float4 w = ldg4(wlast + c0 + q);
+            dot = fmaf(u[q], w.x, dot); dot = fmaf(u[q + 1], w.y, dot); dot = fmaf(u[q + 2], w.z, dot); dot = fmaf(u[q + 3], w.w, dot);
+        }
+    } else {
+        uint32_t hi[8], lo[8];
         split8<NPASS, ACT == ACT_R>(u, hi, lo);
-        const uint32_t off = koff + (uint32_t)(c0 >> 3) * 128u;      // canonical K-major tile: 8 K elements of a row = 16 bytes
-        t3::sts128(ohi + off, hi);
-        if (NPASS == 3) t3::sts128(olo + off, lo);
+        split8<NPASS, ACT == ACT_R>(u + 8, hi + 4, lo + 4);
+        tmem_st8u(acc + (uint32_t)c0, hi);
+        if (NPASS == 3) tmem_st8u(acc + (uint32_t)c0 + 8u, lo);
     }
 }
 
-// hidden-layer epilogue of one net: this thread owns the 8-column chunks part, part + 4, ... of its row
-template <int NPASS, int ACT, bool DOT, bool WRITE>
-__device__ __noinline__ float epi_wide(uint32_t acc, uint32_t ohi, uint32_t olo, const float* __restrict__ bias, const float* __restrict__ wlast,
-                                       int part, int W, uint32_t koff) {
-    float dot = 0.0f;
+// The 16-column groups c0, c0 + 64, ... < cend of this thread.  (Two groups in flight per iteration was tried: 32 live
+// accumulator values + their hi / lo pairs do not fit the register budget of a 640-thread CTA and spill 600 B.)
+template <int NPASS, int ACT, bool DOT>
+__device__ __forceinline__ void epi_span(uint32_t acc, int c0, int cend, const float* __restrict__ bias, const float* __restrict__ wlast, float& dot) {
 #pragma unroll 1
-    for (int c0 = part * 8; c0 < W; c0 += 64) {
-        const int c1 = c0 + 32;
-        const bool two = c1 < W;
-        float v0[8], v1[8];
-        tmem_ld8(acc + (uint32_t)c0, v0);
-        if (two) tmem_ld8(acc + (uint32_t)c1, v1);
-        const float4 b00 = ldg4(bias + c0), b01 = ldg4(bias + c0 + 4);
-        float4 b10 = b00, b11 = b01;
-        if (two) { b10 = ldg4(bias + c1); b11 = ldg4(bias + c1 + 4); }
+    for (; c0 < cend; c0 += 64) {
+        float u[16];
+        tmem_ld16(acc + (uint32_t)c0, u);
         tmem_wait_ld();
-        epi_chunk_w<NPASS, ACT, DOT, WRITE>(v0, c0, b00, b01, wlast, ohi, olo, koff, dot);
-        if (two) epi_chunk_w<NPASS, ACT, DOT, WRITE>(v1, c1, b10, b11, wlast, ohi, olo, koff, dot);
+        epi_math16<NPASS, ACT, DOT>(u, acc, c0, bias, wlast, dot);
+    }
+}
+
+// Epilogue of one net-layer: first half as soon as its MMAs are done, second half after the others (its MMAs ran under
+// the first half's epilogue).  This thread owns the 16-column groups part, part + 4, ... of each half.
+// A converting (non-DOT) layer hands its operand over itself: opnd[0] after the first half (two-half layers), opnd[1] /
+// both at the end; a DOT layer leaves both arrivals to the caller.
+template <int NPASS, int ACT, bool DOT>
+__device__ __noinline__ float epi_wide(XW& x, uint32_t acc, const float* __restrict__ bias, const float* __restrict__ wlast, int W, int n0) {
+    float dot = 0.0f;
+    wait_half(x, 0);
+    epi_span<NPASS, ACT, DOT>(acc, x.part * 16, n0, bias, wlast, dot);
+    if (n0 < W) {
+        if (!DOT) arrive_w(x, 0);
+        wait_half(x, 1);
+        epi_span<NPASS, ACT, DOT>(acc, n0 + x.part * 16, W, bias, wlast, dot);
+        if (!DOT) arrive_w(x, 1);
+    } else if (!DOT) {
+        arrive_w(x, 2);
     }
     return dot;
 }
@@ -440,12 +525,12 @@ __device__ __forceinline__ void tw_compute(const TwStep* __restrict__ steps, con
     XW x;
     x.lane = lane; x.part = warp >> 2; x.row = (warp & 3) * 32 + lane;
     x.tb = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    x.bars = m.bars; x.mma_cnt = 0; x.part_buf = m.part_buf;
-    x.h_hi = smem_u32(m.hbuf); x.h_lo = x.h_hi + m.h_stride;
+    x.bars = m.bars; x.cnt0 = 0; x.cnt1 = 0; x.part_buf = m.part_buf;
     x.tails = tails;
-    const uint32_t tIN_hi = x.tb + (uint32_t)dm.in_hi, tIN_lo = x.tb + (uint32_t)dm.in_lo;
-    const uint32_t tU_hi = x.tb + (uint32_t)dm.u_hi, tU_lo = x.tb + (uint32_t)dm.u_lo;
-    const uint32_t tACC = x.tb, tMU = x.tb + (uint32_t)dm.stash_col;
+    const uint32_t inu_stride = m.inu_stride;
+    const uint32_t tX = x.tb;                                          // region 0: where every L3 / last layer lands
+    // this thread's chunks of the density means: stash[(d0 / 8) * 128 + row] (8 floats), written and re-read by the same thread
+    float* stash = reinterpret_cast<float*>(m.stash) + (size_t)x.row * 8;
     TW_ITEM_BEGIN(MODE)
         long long n = tile * 128 + x.row;
         const bool valid = n < a.N;
@@ -471,8 +556,9 @@ __device__ __forceinline__ void tw_compute(const TwStep* __restrict__ steps, con
     TW_STEP_BEGIN(MODE)
         const int C = ts.C, c = ts.c, Kin = ts.Kin, Ku = ts.Ku, Wd = ts.Wd, CPd = ts.CPd, Hc = ts.Hc;
         if (INV) lacc = 0.0f;       // the sampler reports every step's own log-det term
-        const uint32_t koff_d = (uint32_t)((x.row >> 3) * (Wd >> 3) * 128 + (x.row & 7) * 16);
-        const uint32_t koff_c = (uint32_t)((x.row >> 3) * (Hc >> 3) * 128 + (x.row & 7) * 16);
+        // shared addresses of this row inside the first-layer operand tiles [IN hi, IN lo, U hi, U lo]
+        const uint32_t in_row = smem_u32(m.inu) + (uint32_t)((x.row >> 3) * (Kin >> 3) * 128 + (x.row & 7) * 16);
+        const uint32_t u_row = smem_u32(m.inu) + 2u * inu_stride + (uint32_t)((x.row >> 3) * (Ku >> 3) * 128 + (x.row & 7) * 16);
         int ji = 0;                 // schedule position of the job whose epilogue runs next
         // ---- input operand [z (2), cond (C0), prefix (2*step), 0...] ----
         {
@@ -495,8 +581,8 @@ __device__ __forceinline__ void tw_compute(const TwStep* __restrict__ steps, con
                 }
                 uint32_t hi[4], lo[4];
                 split8<NPASS, false>(v, hi, lo);
-                tmem_st4(tIN_hi + (uint32_t)(k0 >> 1), hi);
-                if (NPASS == 3) tmem_st4(tIN_lo + (uint32_t)(k0 >> 1), lo);
+                t3::sts128(in_row + (uint32_t)(k0 >> 3) * 128u, hi);
+                if (NPASS == 3) t3::sts128(in_row + inu_stride + (uint32_t)(k0 >> 3) * 128u, lo);
             }
         }
         arrive_w(x);
@@ -510,16 +596,27 @@ __device__ __forceinline__ void tw_compute(const TwStep* __restrict__ steps, con
 #pragma unroll 1
                 for (int l = 0; l < 2; ++l) {
                     const float* bias = x.tails + ts.job_tail[tw_img_job(ts, ji, INV)];
+                    const uint32_t acc = x.tb + (uint32_t)ts.job_reg[ji] * kTwRegion;
+                    const int n0 = ts.job_n0[ji];
                     ++ji;
-                    wait_mma_w(x);
-                    epi_wide<NPASS, ACT_R, false, true>(tACC, x.h_hi, x.h_lo, bias, nullptr, x.part, Wd, koff_d);
-                    arrive_w(x);
+                    epi_wide<NPASS, ACT_R, false>(x, acc, bias, nullptr, Wd, n0);      // waits for the halves and hands the operand over itself
                 }
                 const float* b3 = x.tails + ts.job_tail[tw_img_job(ts, ji, INV)];
                 ++ji;
                 if (net == 0) bias_mu = b3; else bias_ls = b3;
-                wait_mma_w(x);
-                if (net == 0) arrive_w(x);      // log-scale net L1: operand IN is in place, the accumulator is free
+                wait_half(x, 0);                 // L3 is narrow (<= 96 columns): one half, lands in region 0
+                if (net == 0) {                  // park the means (+ bias) while the log-scale net runs through both regions
+                    for (int d0 = x.part * 8; d0 < CPd; d0 += 8 * NPARTS) {
+                        float mu[8];
+                        tmem_ld8(tX + (uint32_t)d0, mu);
+                        const float4 ba = ldg4(b3 + d0), bb = ldg4(b3 + d0 + 4);
+                        tmem_wait_ld();
+                        float* sp = stash + (size_t)(d0 >> 3) * 1024;
+                        *reinterpret_cast<float4*>(sp) = make_float4(mu[0] + ba.x, mu[1] + ba.y, mu[2] + ba.z, mu[3] + ba.w);
+                        *reinterpret_cast<float4*>(sp + 4) = make_float4(mu[4] + bb.x, mu[5] + bb.y, mu[6] + bb.z, mu[7] + bb.w);
+                    }
+                    arrive_w(x);                 // log-scale net L1: operand IN is in place, region 0 is free again
+                }
             }
             // ---- L3 outputs: means in the stash, log-stddevs in the accumulator ----
             if (which == 0) {
@@ -540,8 +637,12 @@ __device__ __forceinline__ void tw_compute(const TwStep* __restrict__ steps, con
                         float mu[8], ls[8], e[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) e[i] = 0.0f;
-                        tmem_ld8(tMU + (uint32_t)d0, mu);
-                        tmem_ld8(tACC + (uint32_t)d0, ls);
+                        {
+                            const float* sp = stash + (size_t)(d0 >> 3) * 1024;
+                            const float4 ma = *reinterpret_cast<const float4*>(sp), mb = *reinterpret_cast<const float4*>(sp + 4);
+                            mu[0] = ma.x; mu[1] = ma.y; mu[2] = ma.z; mu[3] = ma.w; mu[4] = mb.x; mu[5] = mb.y; mu[6] = mb.z; mu[7] = mb.w;
+                        }
+                        tmem_ld8(tX + (uint32_t)d0, ls);
                         if (a.eps != nullptr) {
                             const float* ep = a.eps + n * a.eps_rs + (MODE == 1 ? ts.seq_eps_off + (jstep - step) * C : ts.eps_off) + d0;
 #pragma unroll
@@ -553,7 +654,7 @@ __device__ __forceinline__ void tw_compute(const TwStep* __restrict__ steps, con
                         tmem_wait_ld();
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {      // branch-free, see kernels_tc3.cuh (padded columns: mu = ls = 0)
-                            const float mm = mu[i] + __ldg(bias_mu + d0 + i), l = ls[i] + __ldg(bias_ls + d0 + i);
+                            const float mm = mu[i], l = ls[i] + __ldg(bias_ls + d0 + i);
                             const float en = d0 + i < C ? e[i] : 0.0f;
                             u[i] = clamp_h(fmaf(t3::fast_exp(l), en, mm));
                             p_ls += l;
@@ -568,8 +669,8 @@ __device__ __forceinline__ void tw_compute(const TwStep* __restrict__ steps, con
                     }
                     uint32_t hi[4], lo[4];
                     split8<3, false>(u, hi, lo);     // u is always kept as a hi+lo pair: the second density needs it back at full precision
-                    tmem_st4(tU_hi + (uint32_t)(d0 >> 1), hi);
-                    tmem_st4(tU_lo + (uint32_t)(d0 >> 1), lo);
+                    t3::sts128(u_row + (uint32_t)(d0 >> 3) * 128u, hi);
+                    t3::sts128(u_row + inu_stride + (uint32_t)(d0 >> 3) * 128u, lo);
                 }
                 const float s_ls = row_sum_w(x, 0, p_ls), s_e2 = row_sum_w(x, 1, p_e2);
                 const float lp_u = (-0.5f * (float)C * kLog2Pi - s_ls) - 0.5f * s_e2;
@@ -581,17 +682,21 @@ __device__ __forceinline__ void tw_compute(const TwStep* __restrict__ steps, con
                 for (int d0 = x.part * 8; d0 < CPd; d0 += 8 * NPARTS) {
                     float mu[8], ls[8];
                     uint32_t uh[4], ul[4];
-                    tmem_ld8(tMU + (uint32_t)d0, mu);
-                    tmem_ld8(tACC + (uint32_t)d0, ls);
-                    tmem_ld4(tU_hi + (uint32_t)(d0 >> 1), uh);
-                    tmem_ld4(tU_lo + (uint32_t)(d0 >> 1), ul);
+                    {
+                        const float* sp = stash + (size_t)(d0 >> 3) * 1024;
+                        const float4 ma = *reinterpret_cast<const float4*>(sp), mb = *reinterpret_cast<const float4*>(sp + 4);
+                        mu[0] = ma.x; mu[1] = ma.y; mu[2] = ma.z; mu[3] = ma.w; mu[4] = mb.x; mu[5] = mb.y; mu[6] = mb.z; mu[7] = mb.w;
+                    }
+                    tmem_ld8(tX + (uint32_t)d0, ls);
+                    t3::lds128u(u_row + (uint32_t)(d0 >> 3) * 128u, uh);
+                    t3::lds128u(u_row + inu_stride + (uint32_t)(d0 >> 3) * 128u, ul);
                     tmem_wait_ld();
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {      // branch-free: padded columns carry mu = ls = 0 and u is masked
                         const __half2 h2 = *reinterpret_cast<const __half2*>(&uh[i >> 1]), l2 = *reinterpret_cast<const __half2*>(&ul[i >> 1]);
                         const float2 hf = __half22float2(h2), lf = __half22float2(l2);
                         const float u = d0 + i < C ? ((i & 1) ? hf.y + lf.y : hf.x + lf.x) : 0.0f;     // columns C, C+1 of the operand hold mx, not u
-                        const float mm = mu[i] + __ldg(bias_mu + d0 + i), l = ls[i] + __ldg(bias_ls + d0 + i);
+                        const float mm = mu[i], l = ls[i] + __ldg(bias_ls + d0 + i);
                         const float df = (u - mm) * t3::fast_exp(-l);
                         p_q = fmaf(df, df, p_q);
                         p_ls += l;
@@ -615,17 +720,17 @@ __device__ __forceinline__ void tw_compute(const TwStep* __restrict__ steps, con
                     for (int l = 0; l <= ts.n_hidden; ++l) {
                         const bool last = l == ts.n_hidden;
                         const float* tail = x.tails + ts.job_tail[tw_img_job(ts, ji, INV)];
+                        const uint32_t acc = x.tb + (uint32_t)ts.job_reg[ji] * kTwRegion;
+                        const int n0 = ts.job_n0[ji];
                         ++ji;
-                        wait_mma_w(x);
                         if (!last) {
-                            if (net == 0) epi_wide<NPASS, ACT_T, false, true>(tACC, x.h_hi, x.h_lo, tail, nullptr, x.part, Hc, koff_c);
-                            else epi_wide<NPASS, ACT_R, false, true>(tACC, x.h_hi, x.h_lo, tail, nullptr, x.part, Hc, koff_c);
-                            arrive_w(x);
+                            if (net == 0) epi_wide<NPASS, ACT_T, false>(x, acc, tail, nullptr, Hc, n0);
+                            else epi_wide<NPASS, ACT_R, false>(x, acc, tail, nullptr, Hc, n0);
                         } else {
                             float pd;
-                            if (net == 0) pd = epi_wide<NPASS, ACT_T, true, false>(tACC, x.h_hi, x.h_lo, tail, tail + Hc, x.part, Hc, koff_c);
-                            else pd = epi_wide<NPASS, ACT_R, true, false>(tACC, x.h_hi, x.h_lo, tail, tail + Hc, x.part, Hc, koff_c);
-                            if (net == 0) { ps = pd; bs = __ldg(tail + 2 * Hc); arrive_w(x); }   // t-net L0: operand U unchanged, accumulator drained
+                            if (net == 0) pd = epi_wide<NPASS, ACT_T, true>(x, acc, tail, tail + Hc, Hc, n0);
+                            else pd = epi_wide<NPASS, ACT_R, true>(x, acc, tail, tail + Hc, Hc, n0);
+                            if (net == 0) { ps = pd; bs = __ldg(tail + 2 * Hc); arrive_w(x); }   // t-net L0: operand U unchanged, region 0 drained
                             else { pt_ = pd; bt = __ldg(tail + 2 * Hc); }
                         }
                     }
@@ -650,24 +755,24 @@ __device__ __forceinline__ void tw_compute(const TwStep* __restrict__ steps, con
                     }
                 }
                 float p0, p1;
-                uint32_t dst_hi, dst_lo;
+                uint32_t dst_hi;              // shared address of the (hi) pair; the lo pair sits one tile further
                 int owner;
                 if (more) {
                     const int mn = ts.masked_dim[bn];
                     p0 = mn == 0 ? clamp_h(z0) : 0.0f; p1 = mn == 1 ? clamp_h(z1) : 0.0f;
-                    dst_hi = tU_hi + (uint32_t)(C >> 1); dst_lo = tU_lo + (uint32_t)(C >> 1);
+                    dst_hi = u_row + (uint32_t)(C >> 3) * 128u + (uint32_t)(C & 7) * 2u;
                     owner = (C >> 3) % NPARTS;
                 } else {
                     p0 = clamp_h(z0); p1 = clamp_h(z1);
-                    dst_hi = tIN_hi; dst_lo = tIN_lo;
+                    dst_hi = in_row;
                     owner = 0;
                 }
                 if (x.part == owner) {
                     const __half2 h = __floats2half2_rn(p0, p1);
                     const float2 f = __half22float2(h);
                     const __half2 lo2 = __floats2half2_rn(p0 - f.x, p1 - f.y);
-                    tmem_st1(dst_hi, *reinterpret_cast<const uint32_t*>(&h));
-                    tmem_st1(dst_lo, *reinterpret_cast<const uint32_t*>(&lo2));
+                    t3::sts32(dst_hi, *reinterpret_cast<const uint32_t*>(&h));
+                    t3::sts32(dst_hi + inu_stride, *reinterpret_cast<const uint32_t*>(&lo2));
                 }
                 arrive_w(x);
             }
@@ -709,8 +814,10 @@ k_cif_wide(const TwStep* __restrict__ steps, const uint8_t* __restrict__ img, co
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) {
         for (int s = 0; s < dm.nslots; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-        mbar_init(&bars->mma_done, 1);
-        mbar_init(&bars->opnd, 16);
+        mbar_init(&bars->done[0], 1);
+        mbar_init(&bars->done[1], 1);
+        mbar_init(&bars->opnd[0], 16);
+        mbar_init(&bars->opnd[1], 16);
         mbar_fence_init();
     }
     if (warp == 16) tmem_alloc(tslot, 512);
@@ -741,7 +848,7 @@ inline int tcw_launch(TwDims dm, const TwStep* d_steps, const unsigned char* d_i
                       int mode, int num_sms, int smem_optin, cudaStream_t stream, uint64_t* launches, std::string* msg) {
     if (!dm.supported || d_img == nullptr) {
         *msg = "the tensor-core path does not support this model shape (needs hidden_size % 16 == 0, hidden_size <= 256, an even "
-               "cond_size, and widest layer + padded cond width + 2 x padded input width <= 512 tensor-memory columns); use FC_PREC_FP32";
+               "cond_size and 2 * (cond_size + 2 * pred_len) <= 256); use FC_PREC_FP32";
         return 1;
     }
     const int T = dm.T;
