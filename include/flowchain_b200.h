@@ -59,9 +59,8 @@ enum { FC_PREC_FP32 = 0,    /* CUDA-core fp32, parity 1e-4 (+rel) nats          
  *   - every layer <= 80 wide (hidden_size <= 80 and 2*(cond_size + 2*pred_len) <= 80, e.g. the default ETH model):
  *     two resident 128-row tiles per CTA (csrc/kernels_tc3.cuh);
  *   - wider, up to hidden_size 256 / cond_size 64 (BASELINE config 5, the reference's tuning range
- *     src/main.py:222-229), as long as  max(hidden_size, W) + pad16(C) + 2*pad16(C + 2) <= 512  tensor-memory columns
- *     with C = cond_size + 2*(pred_len - 1), W = pad16(2*(C + 2)): one tile per CTA, K-slab weight streaming
- *     (csrc/kernels_tcw.cuh);
+ *     src/main.py:222-229), as long as  2*(cond_size + 2*pred_len) <= 256  (two 256-column tensor-memory regions):
+ *     one tile per CTA, in-place accumulator -> operand conversion, K-slab weight streaming (csrc/kernels_tcw.cuh);
  * other shapes return an error that names FC_PREC_FP32. */
 
 /* prefix modes of the dense-grid evaluation */
