@@ -199,9 +199,8 @@ __device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t r) {
 __device__ __forceinline__ float clamp_h(float v) { return fminf(fmaxf(v, -65000.0f), 65000.0f); }
 
 // 8 fp32 values -> 4 packed fp16 pairs (hi) and the 4 packed residual pairs (lo), with an optional fused ReLU.
-// NPASS = 3: hi is the value TRUNCATED to fp16's 11 significant bits (one LOP3 on the integer pipe; exactly
-// representable, so the pack is exact), lo = a - hi in fp32 (same sign as a), both packed with
-// F2FP[.RELU][.SATFINITE] -- ReLU and the fp16 overflow clamp ride on the pack instruction for free.
+// NPASS = 3: hi = fp16(a), lo = fp16(a - hi): F2FP pack (2 values), one FHFMA per value (mixed-precision FMA,
+// hi x (-1.0h) + a, exact), F2FP pack -- 2 instructions per value; ReLU and the fp16 overflow clamp ride on the packs.
 // NPASS = 1: hi is the value rounded to fp16.
 template <int NPASS, bool RELU>
 __device__ __forceinline__ void split8(const float* a, uint32_t* hi, uint32_t* lo) {
@@ -209,15 +208,16 @@ __device__ __forceinline__ void split8(const float* a, uint32_t* hi, uint32_t* l
     for (int i = 0; i < 4; ++i) {
         const float a0 = a[2 * i], a1 = a[2 * i + 1];
         if (NPASS == 3) {
-            const float h0 = __uint_as_float(__float_as_uint(a0) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(a1) & 0xFFFFE000u);
-            const float l0 = a0 - h0, l1 = a1 - h1;
-            if (RELU) {
-                asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi[i]) : "f"(h1), "f"(h0));
-                asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo[i]) : "f"(l1), "f"(l0));
-            } else {
-                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi[i]) : "f"(h1), "f"(h0));
-                asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo[i]) : "f"(l1), "f"(l0));
-            }
+            // hi = fp16(a) (toward zero under ReLU, so that the remainder of a positive value is >= 0 and the remainder
+            // of a negative one -- hi = 0, lo = a -- is cleared by the second .relu); lo = a - hi is exact in fp32 and
+            // costs ONE mixed-precision FMA per value (FHFMA: f16 x f16 + f32), 2 instructions per value in all.
+            float l0, l1;
+            if (RELU) asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi[i]) : "f"(a1), "f"(a0));
+            else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi[i]) : "f"(a1), "f"(a0));
+            asm("{.reg .b16 x, y, m;\n\tmov.b32 {x, y}, %2;\n\tmov.b16 m, 0xBC00;\n\t"      // m = -1.0h
+                "fma.rn.f32.f16 %0, x, m, %3;\n\tfma.rn.f32.f16 %1, y, m, %4;}" : "=f"(l0), "=f"(l1) : "r"(hi[i]), "f"(a0), "f"(a1));
+            if (RELU) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo[i]) : "f"(l1), "f"(l0));
+            else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo[i]) : "f"(l1), "f"(l0));
         } else {
             if (RELU) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi[i]) : "f"(a1), "f"(a0));
             else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi[i]) : "f"(a1), "f"(a0));
