@@ -13,32 +13,26 @@
 #include "kernels_fp32.cuh"
 #include "tc_f16x3.cuh"
 
-// FC_T3_SPLIT_NETS = 1: inside a tile, column part p (4 warps) runs the hidden-layer epilogues of NET p only, over all
-// columns of its rows -- the s-net (tanh, XU-bound) and t-net (ReLU) chains of a tile advance on different warps instead
-// of taking turns on the same eight.  0: the round-1 schedule (both parts share every epilogue, nets in turn).
-// Measured on B200 (config 2): 50.5 ms with the split vs 49.3 ms without -- the tanh chain alone on four warps is
-// latency-bound, so the default stays 0; kept as a build option.
-#ifndef FC_T3_SPLIT_NETS
-#define FC_T3_SPLIT_NETS 0
-#endif
 
 namespace fc {
 
 // tensor-memory column map of one tile (256 columns per tile), two layouts:
 //  HTS = false (layers up to 80 wide, chain mode, sampler): accumulators + the narrow FIRST-layer operands in tensor
 //        memory (TS-mode MMAs), hidden-layer operands in shared memory (SS-mode MMAs);
-//  HTS = true  (per-step launches whose layers are all <= 64 wide): accumulators + the HIDDEN-layer operands (hi, lo of
-//        both nets, K <= 64) in tensor memory, first-layer operands (K <= 32) in shared memory.  An SS-mode MMA pays
-//        ~44 cycles for reading its [128 x 16] A tile from shared memory on top of the N/2 cycles of math (measured,
-//        tools/mb_mma.cu: N = 64: 76 cycles SS vs 43 TS); the hidden layers are 80 % of the MMAs, so they get the TS slot.
+//  HTS = true  (per-step launches whose layers are all <= 64 wide): hidden-layer operands in tensor memory, first-layer
+//        operands (K <= 32) in shared memory.  An SS-mode MMA pays ~44 cycles for reading its [128 x 16] A tile from
+//        shared memory on top of the N/2 cycles of math (measured, tools/mb_mma.cu: N = 64: 76 cycles SS vs 43 TS); the
+//        hidden layers are 80 % of the MMAs, so they get the TS slot.  Each net owns TWO 64-column regions that its
+//        jobs use in turn (job k accumulates into region k & 1): the epilogue converts the 16 accumulator columns of a
+//        K-step IN PLACE into that K-step's fp16 operand (hi: 8 columns, lo: the next 8), and the next job reads it
+//        from there while accumulating into the other region.
 constexpr uint32_t kT3Acc0 = 0, kT3Acc1 = 80;            // HTS = false: fp32 accumulators of net 0 / 1 (N <= 80)
 constexpr uint32_t kT3InHi = 160, kT3InLo = 184;         // [z|w, cond, prefix] operand, K <= 48
 constexpr uint32_t kT3UHi = 208, kT3ULo = 232;           // [u, mx] operand, K <= 48
-constexpr uint32_t kT3HAcc1 = 64;                        // HTS = true: accumulators [0, 64), [64, 128)
-constexpr uint32_t kT3H0Hi = 128, kT3H0Lo = 160, kT3H1Hi = 192, kT3H1Lo = 224;   // hidden operands of net 0 / 1, K <= 64
+constexpr uint32_t kT3NetCols = 128, kT3RegCols = 64;   // HTS = true: net n, job parity r -> columns [128 n + 64 r, + 64)
 constexpr int kT3InuK = 32;                              // HTS = true: widest first-layer operand, [128 x 32] fp16 tiles in smem
 constexpr uint32_t kT3TileCols = 256;
-constexpr int kT3Threads = 16 * 32 + 128;                 // 2 x 8 compute warps + a service warpgroup (producer, 2 issuers, 1 idle)
+constexpr int kT3Threads = 16 * 32 + 128;                 // 2 x 8 compute warps + a service warpgroup: 4 MMA issuers (net x tile)
 constexpr int kT3ComputeRegs = 104, kT3ServiceRegs = 56;   // setmaxnreg split of the register file (see the kernel)
 constexpr int kT3OnesOff = 12288;                         // constant [128 x 16] fp16 tile, columns 0..2 = 1 (bias fold)
 constexpr int kT3Header = 16384;                          // barriers, step table, row-partial buffers, bias ring, ones tile
@@ -125,11 +119,9 @@ __device__ __forceinline__ void epi_chunk3(float* u, int c0, const float4 b0, co
 
 // koff = (row/8) * (W/8) * 128 + (row%8) * 16 : byte offset of this thread's row inside a [128 x W] canonical tile
 // BIAS = false: the bias is already inside the accumulator (folded chunk, see the issuer)
-// ALLCOLS: the thread owns every 8-column chunk of its row (one net per column part, see FC_T3_SPLIT_NETS) instead of
-// every other one
-template <int NPASS, int ACT, bool DOT, bool WRITE, bool BIAS, bool HTS = false, bool ALLCOLS = false>
+template <int NPASS, int ACT, bool DOT, bool WRITE, bool BIAS, bool HTS = false>
 __device__ __noinline__ float epi_hidden3(uint32_t acc, uint32_t ohi, uint32_t olo, uint32_t bias, uint32_t wlast, int part, int W, uint32_t koff) {
-    constexpr int CSTEP = ALLCOLS ? 8 : 16;
+    constexpr int CSTEP = 16;
     float dot = 0.0f;
 #pragma unroll 1
     for (int c0 = part * 8; c0 < W; c0 += 2 * CSTEP) {
@@ -153,9 +145,9 @@ __device__ __noinline__ float epi_hidden3(uint32_t acc, uint32_t ohi, uint32_t o
 // Epilogue of a layer that is exactly 16 * NB columns wide: this thread's NB chunks are processed in unguarded pairs,
 // so the compiler interleaves the 16 independent value chains of a pair (the guarded loop above keeps every chunk in
 // its own basic block); all NB at once measured slower than pairs.
-template <int NPASS, int ACT, bool DOT, bool WRITE, bool BIAS, int NB, bool HTS = false, bool ALLCOLS = false>
+template <int NPASS, int ACT, bool DOT, bool WRITE, bool BIAS, int NB, bool HTS = false>
 __device__ __noinline__ float epi_hidden3_nb(uint32_t acc, uint32_t ohi, uint32_t olo, uint32_t bias, uint32_t wlast, int part, uint32_t koff) {
-    constexpr int CSTEP = ALLCOLS ? 8 : 16;
+    constexpr int CSTEP = 16;
     float dot = 0.0f;
     const int c0 = part * 8;
 #pragma unroll
@@ -177,18 +169,10 @@ __device__ __noinline__ float epi_hidden3_nb(uint32_t acc, uint32_t ohi, uint32_
 }
 template <int NPASS, int ACT, bool DOT, bool WRITE, bool BIAS, bool HTS = false>
 __device__ __forceinline__ float epi_layer3(uint32_t acc, uint32_t ohi, uint32_t olo, uint32_t bias, uint32_t wlast, int part, int W, uint32_t koff) {
-#if FC_T3_SPLIT_NETS
-    // one net per column part: the thread walks all W columns of its row (`part` only selected the net)
-    if (W == 64) return epi_hidden3_nb<NPASS, ACT, DOT, WRITE, BIAS, 8, HTS, true>(acc, ohi, olo, bias, wlast, 0, koff);
-    if (W == 48) return epi_hidden3_nb<NPASS, ACT, DOT, WRITE, BIAS, 6, HTS, true>(acc, ohi, olo, bias, wlast, 0, koff);
-    if (!HTS && W == 80) return epi_hidden3_nb<NPASS, ACT, DOT, WRITE, BIAS, 10, HTS, true>(acc, ohi, olo, bias, wlast, 0, koff);
-    return epi_hidden3<NPASS, ACT, DOT, WRITE, BIAS, HTS, true>(acc, ohi, olo, bias, wlast, 0, W, koff);
-#else
     if (W == 64) return epi_hidden3_nb<NPASS, ACT, DOT, WRITE, BIAS, 4, HTS>(acc, ohi, olo, bias, wlast, part, koff);
     if (W == 48) return epi_hidden3_nb<NPASS, ACT, DOT, WRITE, BIAS, 3, HTS>(acc, ohi, olo, bias, wlast, part, koff);
     if (!HTS && W == 80) return epi_hidden3_nb<NPASS, ACT, DOT, WRITE, BIAS, 5, HTS>(acc, ohi, olo, bias, wlast, part, koff);
     return epi_hidden3<NPASS, ACT, DOT, WRITE, BIAS, HTS>(acc, ohi, olo, bias, wlast, part, W, koff);
-#endif
 }
 // e^x = 2^(x log2 e) on the MUFU (2 ulp; denormal results flush to zero, which only ever multiplies the noise)
 __device__ __forceinline__ float fast_exp(float x) {
@@ -218,10 +202,15 @@ struct X3 {
 };
 
 __device__ __forceinline__ const uint8_t* slot_ptr3(const X3& x, uint32_t it) { return x.slots + (size_t)(it & x.nslots_mask) * x.slot_bytes; }
-__device__ __forceinline__ void wait_mma3(X3& x, int net) {
-    if (net == 0) { mbar_wait(&x.bars->mma_done[x.g][0], x.mma_cnt0 & 1u); x.mma_cnt0++; }
-    else { mbar_wait(&x.bars->mma_done[x.g][1], x.mma_cnt1 & 1u); x.mma_cnt1++; }
+// waits for the next job of `net` and returns the tensor-memory address of its accumulator (HTS: the region alternates)
+template <bool HTS>
+__device__ __forceinline__ uint32_t wait_mma3(X3& x, int net) {
+    uint32_t cnt;
+    if (net == 0) { cnt = x.mma_cnt0++; mbar_wait(&x.bars->mma_done[x.g][0], cnt & 1u); }
+    else { cnt = x.mma_cnt1++; mbar_wait(&x.bars->mma_done[x.g][1], cnt & 1u); }
     tc_fence_after();
+    if (HTS) return x.tb + (uint32_t)net * kT3NetCols + (cnt & 1u) * kT3RegCols;
+    return x.tb + (net ? kT3Acc1 : kT3Acc0);
 }
 // this warp's tensor-memory accesses and shared-memory operand stores are complete -> tell the issuers
 __device__ __forceinline__ void warp_arrive3(const X3& x, uint64_t* bar) {
@@ -231,6 +220,41 @@ __device__ __forceinline__ void warp_arrive3(const X3& x, uint64_t* bar) {
     tc_fence_before();
     __syncwarp();
     if (x.lane == 0) mbar_arrive(bar);
+}
+// HTS epilogue of one net-layer.  The thread (row, column part p) owns the K-steps p, p + 2, ... of the NEXT layer: it
+// loads the 16 accumulator columns of a K-step, applies the activation and writes the hi / lo fp16 operand of that
+// K-step over them (hi: columns [16 ks, +8), lo: [16 ks + 8, +8) -- exactly what a TS-mode MMA reads), then arrives on
+// `done`.  No shared memory is written, so the arrival needs no fence.proxy.async (a MEMBAR.ALL.CTA in the SASS).
+// (Letting the next job start on the first two K-steps while the last ones are still being converted was tried -- an
+// extra arrival per layer and a two-stage issue -- and measured slower, 48.7 vs 46.4 ms: the tensor pipe is busy with
+// the other three job streams at that moment anyway.)
+template <int NPASS, int ACT, bool DOT, bool WRITE, bool BIAS>
+__device__ __noinline__ float epi_inplace3(const X3& x, uint32_t acc, uint32_t bias, uint32_t wlast, int W, uint64_t* done) {
+    float dot = 0.0f;
+    const int nk = W >> 4;
+#pragma unroll 1
+    for (int ks = x.part; ks < nk; ks += 2) {
+        const int c0 = ks * 16;
+        float v[16];
+        tmem_ld16(acc + (uint32_t)c0, v);
+        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0, b2 = b0, b3 = b0;
+        if (BIAS) {
+            b0 = lds128(bias + (uint32_t)c0 * 4); b1 = lds128(bias + (uint32_t)c0 * 4 + 16);
+            b2 = lds128(bias + (uint32_t)c0 * 4 + 32); b3 = lds128(bias + (uint32_t)c0 * 4 + 48);
+        }
+        tmem_wait_ld();
+        // epi_chunk3 stores 4 packed columns at ohi + col / 2: ohi = acc + c0 / 2 puts the two chunks at acc + c0 + {0, 4}
+        const uint32_t ohi = acc + (uint32_t)(c0 >> 1), olo = ohi + 8u;
+        epi_chunk3<NPASS, ACT, DOT, WRITE, BIAS, true>(v, c0, b0, b1, wlast, ohi, olo, 0u, dot);
+        epi_chunk3<NPASS, ACT, DOT, WRITE, BIAS, true>(v + 8, c0 + 8, b2, b3, wlast, ohi, olo, 0u, dot);
+    }
+    if (WRITE) {
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (x.lane == 0) mbar_arrive(done);
+    }
+    return dot;
 }
 __device__ __forceinline__ float row_sum3(const X3& x, int slot, float v) {      // slot in {0, 1}
     x.part_buf[(slot * 2 + x.part) * 128 + x.row] = v;
@@ -300,45 +324,6 @@ __device__ __forceinline__ int t3_chunk_of_job(const T2Step& ts, int ci, bool in
     return ci - nb6;
 }
 
-// ===== fourth warp of the service warpgroup: only takes part in the CTA-wide step-table reloads =====
-__device__ __forceinline__ void t3_idle(const T2Step* __restrict__ steps, const T3Dims& dm, long long pairs_per_step, long long total_items,
-                                        uint8_t* smem) {
-    const T3Smem m = t3_smem(smem, dm);
-    T3_ITEM_BEGIN(dm.seq)
-    T3_STEP_BEGIN(dm.seq)
-        (void)ts;
-    T3_STEP_END
-    T3_ITEM_END
-}
-
-// ===== weight producer (one warp): streams the step's chunks through the ring =====
-__device__ __forceinline__ void t3_producer(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img, const T3Dims& dm,
-                                         long long pairs_per_step, long long total_items, uint8_t* smem) {
-    const T3Smem m = t3_smem(smem, dm);
-    Bars3* bars = m.bars;
-    uint8_t* slots = m.slots;
-    const uint32_t smask = m.smask;
-    const int lane = threadIdx.x & 31;
-    uint32_t ring_it = 0;
-    int trace_n = 0; (void)trace_n;
-    T3_ITEM_BEGIN(dm.seq)
-    T3_STEP_BEGIN(dm.seq)
-        for (int ci = 0; ci < ts.nchunks; ++ci, ++ring_it) {
-            if (lane == 0) {
-                const uint32_t slot = ring_it & smask;
-                T3_TR(0x50 + (ci & 1))      // producer: wants a slot for chunk ci
-                mbar_wait(&bars->empty[slot], ((ring_it >> dm.nslots_log2) & 1u) ^ 1u);
-                T3_TR(0x52 + (ci & 1))      // slot free: bulk copy issued
-                const int pc = t3_chunk_of_job(ts, ci, dm.seq == 2);
-                mbar_expect_tx(&bars->full[slot], (uint32_t)ts.chunk_bytes[pc]);
-                bulk_load(slots + (size_t)slot * dm.slot_bytes, img + ts.chunk_off[pc], (uint32_t)ts.chunk_bytes[pc], &bars->full[slot]);
-            }
-            __syncwarp();
-        }
-    T3_STEP_END
-    T3_ITEM_END
-}
-
 // All MMAs of one job (= net-layer of one tile): D = A_hi W_hi + A_lo W_hi + A_hi W_lo over NK K-steps of 16.
 // TS: A operand in tensor memory (columns ta_hi / ta_lo, 8 columns per K-step); otherwise shared-memory descriptors.
 template <int NPASS, int NK, bool TS>
@@ -384,8 +369,31 @@ __device__ __forceinline__ void issue_job_loop(int nk, uint32_t acc, uint32_t ta
     }
 }
 
-// ===== MMA issuers, one warp per net; every net-layer is issued for tile 0 then tile 1 from the same weight chunk.
-// First layers read their operand from tensor memory (TS), hidden layers from shared memory (SS). =====
+// K-steps [KLO, KHI) of a job whose A operand sits in the in-place HTS layout (K-step ks: hi at ta + 16 ks, lo 8 further)
+template <int NPASS, int KLO, int KHI>
+__device__ __forceinline__ void issue_inplace(uint32_t acc, uint32_t ta, uint64_t dhi, uint64_t dlo, uint32_t idesc, uint32_t acc0) {
+#pragma unroll
+    for (int ks = KLO; ks < KHI; ++ks) umma_ts(acc, ta + ks * 16, dhi + (uint64_t)(ks * 16), idesc, ks > 0 ? 1u : acc0);
+    if (NPASS == 3) {
+#pragma unroll
+        for (int ks = KLO; ks < KHI; ++ks) umma_ts(acc, ta + ks * 16 + 8, dhi + (uint64_t)(ks * 16), idesc, 1u);
+#pragma unroll
+        for (int ks = KLO; ks < KHI; ++ks) umma_ts(acc, ta + ks * 16, dlo + (uint64_t)(ks * 16), idesc, 1u);
+    }
+}
+
+// ===== MMA issuers, one warp per (net, tile): four independent job streams.  Measured with the event trace
+// (tools/t3_trace.py): a service warp retires roughly one instruction per 8-10 cycles (a dependent scalar stream next to
+// four busy epilogue warps), so with ONE issuer per net the per-chunk bookkeeping plus the issue of two tiles' jobs took
+// 3.7 k cycles and paced the whole pipeline; per (net, tile) the same work has a full layer period to itself.
+// The issuer of a net's LAST tile also feeds that net's half of the weight ring: at the top of iteration k it requests
+// the chunks below k + D (D = ring slots per net), each as two bulk copies on the slot's `full` barrier -- the chunk into
+// the slot and its fp32 tail (biases, last-row vector) straight into the bias ring entry [net][job & 3], so that the
+// epilogues keep the tail after the slot has been handed back and no warp copies it.  A slot is handed back by the
+// tcgen05.commit of the MMAs that read it (`empty` counts the tiles).  With one step per item the requests run on into
+// the next item of the same step.
+// First layers read their operand from tensor memory (TS) and hidden layers from shared memory (SS), or the other way
+// round under HTS. =====
 template <int NPASS, bool TS>
 __device__ __forceinline__ void issue_dispatch(int nk, uint32_t acc, uint32_t ta_hi, uint32_t ta_lo, uint64_t ahi, uint64_t alo, uint64_t dhi,
                                                uint64_t dlo, uint32_t idesc, uint32_t acc0) {
@@ -400,87 +408,115 @@ __device__ __forceinline__ void issue_dispatch(int nk, uint32_t acc, uint32_t ta
 }
 
 template <int NPASS, bool HTS>
-__device__ __forceinline__ void t3_issuer(const T2Step* __restrict__ steps, const T3Dims& dm, long long pairs_per_step, long long total_items,
-                                       uint8_t* smem, uint32_t tmem_base, int net) {
+__device__ __forceinline__ void t3_issuer(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img, const T3Dims& dm,
+                                       long long pairs_per_step, long long total_items, uint8_t* smem, uint32_t tmem_base, int net, int t) {
     const T3Smem m = t3_smem(smem, dm);
     Bars3* bars = m.bars;
-    uint8_t *slots = m.slots, *hbuf = m.hbuf, *bias_ring = m.bias_ring;
+    uint8_t *slots = m.slots, *hbuf = m.hbuf;
     const uint32_t smask = m.smask, h_stride = m.h_stride;
-    const int lane = threadIdx.x & 31;
     uint32_t ring_it = 0;
-    uint32_t opnd_c0 = 0, opnd_c1 = 0, fin_c0 = 0, fin_c1 = 0;    // per-tile phase counters
+    uint32_t opnd_c = 0, fin_c = 0, jobc = 0;      // phase counters of this tile; jobs of this (net, tile) so far
     int trace_n = 0; (void)trace_n;
     const int ntile = dm.single ? 1 : 2;
+    const bool active = t < ntile;                                // one tile per item: the tile-1 issuers only follow the step reloads
+    const bool producer = t == ntile - 1;
+    const int depth = 1 << (dm.nslots_log2 - 1);                  // ring slots of this net
+    int carried = 0;                                              // chunks of the coming step already requested (previous item)
+    const uint32_t tb0 = tmem_base + (uint32_t)t * kT3TileCols;
+    const uint64_t d_ones = umma_desc(smem_u32(m.ones), 128, 256u);
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(leader));
     T3_ITEM_BEGIN(dm.seq)
     T3_STEP_BEGIN(dm.seq)
         const uint32_t base = ring_it;
+        ring_it += (uint32_t)ts.nchunks;
+        if (!active) continue;
+        const int nq = ts.nchunks >> 1;                           // chunks of this net in the step
+        // may the requests run on into the next item?  (same step table: one step per item, the next item exists and is of this step)
+        const bool wrap_ok = nsteps == 1 && item + gridDim.x < total_items && (item + gridDim.x) / pairs_per_step == item / pairs_per_step;
+        int k_req = carried;
+        carried = 0;
 #pragma unroll 1
-        for (int ci = net; ci < ts.nchunks; ci += 2) {
-            const uint32_t it = base + (uint32_t)ci;
-            mbar_wait(&bars->full[it & smask], (it >> dm.nslots_log2) & 1u);
-            T3_TR(0x20)              // weight chunk landed
-            const int w = ts.job_wait[ci], src = ts.job_src[ci], Kp = ts.job_kp[ci], N = ts.job_n[ci];
-            const bool has_bias_tile = ts.job_fold[ci] != 0, fold = has_bias_tile && !dm.no_fold;
-            const int chunk_bytes = ts.chunk_bytes[t3_chunk_of_job(ts, ci, dm.seq == 2)];
-            const uint8_t* chunk = slots + (size_t)(it & smask) * dm.slot_bytes;
-            const uint32_t b_hi = smem_u32(chunk);
-            {   // the fp32 tail (biases, last-row vector) moves to the bias ring so that the weight slot can be handed
-                // back as soon as the MMAs that read it complete (tcgen05.commit -> empty), not after the epilogue
-                const int tiles_b = (NPASS == 3 ? 2 : 1) * N * Kp * 2;
-                const int n16 = (chunk_bytes - tiles_b - (has_bias_tile ? N * 32 : 0)) >> 4;
-                const float4* srcp = reinterpret_cast<const float4*>(chunk + tiles_b);
-                float4* dstp = reinterpret_cast<float4*>(bias_ring + (size_t)(net * 4 + ((it >> 1) & 3)) * kT3BiasEntry);
-                for (int q = lane; q < n16; q += 32) dstp[q] = srcp[q];
-                __syncwarp();
+        for (int ci = net, k = 0; ci < ts.nchunks; ci += 2, ++k, ++jobc) {
+            if (producer) {
+                int target = k + depth;
+                if (!wrap_ok && target > nq) target = nq;
+#pragma unroll 1
+                for (; k_req < target; ++k_req) {
+                    const int rci = net + 2 * (k_req < nq ? k_req : k_req - nq);
+                    const uint32_t rit = base + (k_req < nq ? 0u : (uint32_t)ts.nchunks) + (uint32_t)rci;
+                    const uint32_t slot = rit & smask;
+                    T3_TR(0x50 + net)       // wants the slot for chunk rci
+                    mbar_wait(&bars->empty[slot], ((rit >> dm.nslots_log2) & 1u) ^ 1u);
+                    T3_TR(0x52 + net)       // slot free: bulk copies issued
+                    if (leader) {
+                        const int pc = t3_chunk_of_job(ts, rci, dm.seq == 2);
+                        const int rn = ts.job_n[rci], rk = ts.job_kp[rci];
+                        const uint32_t tiles_b = (uint32_t)(NPASS == 3 ? 2 : 1) * (uint32_t)(rn * rk * 2);
+                        const uint32_t tail_b = (uint32_t)ts.chunk_bytes[pc] - tiles_b - (ts.job_fold[rci] ? (uint32_t)rn * 32u : 0u);
+                        mbar_expect_tx(&bars->full[slot], (uint32_t)ts.chunk_bytes[pc] + tail_b);
+                        bulk_load(slots + (size_t)slot * dm.slot_bytes, img + ts.chunk_off[pc], (uint32_t)ts.chunk_bytes[pc], &bars->full[slot]);
+                        bulk_load(m.bias_ring + (size_t)(net * 4 + ((rit >> 1) & 3)) * kT3BiasEntry, img + ts.chunk_off[pc] + tiles_b, tail_b,
+                                  &bars->full[slot]);
+                    }
+                    __syncwarp();
+                }
             }
+            const uint32_t it = base + (uint32_t)ci;
+            const int w = ts.job_wait[ci], src = ts.job_src[ci], Kp = ts.job_kp[ci], N = ts.job_n[ci];
+            const bool fold = ts.job_fold[ci] != 0 && !dm.no_fold;
+            const int chunk_bytes = ts.chunk_bytes[t3_chunk_of_job(ts, ci, dm.seq == 2)];
+            const uint32_t b_hi = smem_u32(slots + (size_t)(it & smask) * dm.slot_bytes);
             const uint32_t idesc = umma_idesc_f16(128, N), sbo = (uint32_t)(Kp >> 3) * 128u;
             const uint64_t dhi = umma_desc(b_hi, 128, sbo), dlo = umma_desc(b_hi + (uint32_t)(N * Kp * 2), 128, sbo);
             const int nk = Kp >> 4;
             // folded bias: acc = ones[128 x 16] * bias_tile[N x 16]^T first, everything else accumulates on top
-            const uint64_t d_ones = umma_desc(smem_u32(m.ones), 128, 256u);
             const uint64_t d_bias = umma_desc(b_hi + (uint32_t)(chunk_bytes - N * 32), 128, 256u);
             const uint32_t acc0 = fold ? 1u : 0u;
-            uint32_t leader;
-            asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(leader));
-#pragma unroll 1
-            for (int t = 0; t < ntile; ++t) {
-                const uint32_t tb0 = tmem_base + (uint32_t)t * kT3TileCols;
-                // operand of the job: tensor memory (TS) or shared memory (SS), by layout (see the column map)
-                const uint32_t acc = tb0 + (net ? (HTS ? kT3HAcc1 : kT3Acc1) : kT3Acc0);
-                const bool ts_job = HTS ? src == 2 : src < 2;
-                const uint32_t ta_hi = tb0 + (HTS ? (net ? kT3H1Hi : kT3H0Hi) : (src == 0 ? kT3InHi : kT3UHi));
-                const uint32_t ta_lo = tb0 + (HTS ? (net ? kT3H1Lo : kT3H0Lo) : (src == 0 ? kT3InLo : kT3ULo));
-                const uint32_t sa = smem_u32(hbuf) + (uint32_t)(t * 4 + (HTS ? src : net) * 2) * h_stride;
-                const uint64_t ahi = umma_desc(sa, 128, sbo), alo = umma_desc(sa + h_stride, 128, sbo);
-                // ---- critical path: operand of this tile ready -> MMAs -> commit ----
-                if (w == 3) {
-                    if (t == 0) { mbar_wait(&bars->fin[0], fin_c0 & 1u); fin_c0++; }
-                    else { mbar_wait(&bars->fin[1], fin_c1 & 1u); fin_c1++; }
+            // HTS: job k of this net accumulates into region k & 1 and reads the operand its predecessor's epilogue left in
+            // the other one; first-layer jobs read the [IN | U] tiles from shared memory.  Otherwise: accumulators and the
+            // narrow first-layer operands in tensor memory, hidden operands in shared memory.
+            const uint32_t acc = HTS ? tb0 + (uint32_t)net * kT3NetCols + (jobc & 1u) * kT3RegCols : tb0 + (net ? kT3Acc1 : kT3Acc0);
+            const uint32_t ta = tb0 + (uint32_t)net * kT3NetCols + ((jobc & 1u) ^ 1u) * kT3RegCols;
+            const uint32_t ta_hi = tb0 + (src == 0 ? kT3InHi : kT3UHi), ta_lo = tb0 + (src == 0 ? kT3InLo : kT3ULo);
+            const uint32_t sa = smem_u32(hbuf) + (uint32_t)(t * 4 + (HTS ? src : net) * 2) * h_stride;
+            const uint64_t ahi = umma_desc(sa, 128, sbo), alo = umma_desc(sa + h_stride, 128, sbo);
+            T3_TR(0x22)              // descriptors built: waiting for the weight chunk, then the operand
+            mbar_wait(&bars->full[it & smask], (it >> dm.nslots_log2) & 1u);
+            T3_TR(0x20)              // weight chunk landed
+            // ---- critical path: operand of this tile ready -> MMAs -> commit ----
+            if (w == 3) { mbar_wait(&bars->fin[t], fin_c & 1u); fin_c++; }
+            else { mbar_wait(&bars->opnd[t][net], opnd_c & 1u); opnd_c++; }
+            tc_fence_after();
+            T3_TR(0x30 + t)          // operand of the tile ready
+            // straight-line issue for the K widths that occur (16 * nk): with compile-time operand offsets the MMAs of a job
+            // go out back to back (UTCHMMA after UTCHMMA); a counted loop costs ~10 set-up instructions per MMA.
+            if (leader) {
+                if (fold) umma_bf16(acc, d_ones, d_bias, idesc, 0u);
+                if (HTS) {
+                    if (src == 2) {
+                        switch (nk) {
+                            case 1: issue_inplace<NPASS, 0, 1>(acc, ta, dhi, dlo, idesc, acc0); break;
+                            case 2: issue_inplace<NPASS, 0, 2>(acc, ta, dhi, dlo, idesc, acc0); break;
+                            case 3: issue_inplace<NPASS, 0, 3>(acc, ta, dhi, dlo, idesc, acc0); break;
+                            default: issue_inplace<NPASS, 0, 4>(acc, ta, dhi, dlo, idesc, acc0); break;
+                        }
+                    } else issue_dispatch<NPASS, false>(nk, acc, 0, 0, ahi, alo, dhi, dlo, idesc, acc0);
                 } else {
-                    if (t == 0) { mbar_wait(&bars->opnd[0][net], opnd_c0 & 1u); opnd_c0++; }
-                    else { mbar_wait(&bars->opnd[1][net], opnd_c1 & 1u); opnd_c1++; }
-                }
-                tc_fence_after();
-                T3_TR(0x30 + t)          // operand of tile t ready
-                if (leader) {
-                    if (fold) umma_bf16(acc, d_ones, d_bias, idesc, 0u);
-                    // straight-line issue for the K widths that occur (16 * nk): with compile-time operand offsets the
-                    // MMAs of a job go out back to back (UTCHMMA after UTCHMMA).  A counted loop costs ~10 set-up
-                    // instructions per MMA in its remainder iterations -- measured ~69 cycles per MMA against the 32 the
-                    // tensor pipe needs at N = 64, i.e. the issue, not the pipe, paced every MMA -> epilogue hand-off.
-                    if (ts_job) issue_dispatch<NPASS, true>(nk, acc, ta_hi, ta_lo, 0, 0, dhi, dlo, idesc, acc0);
+                    if (src < 2) issue_dispatch<NPASS, true>(nk, acc, ta_hi, ta_lo, 0, 0, dhi, dlo, idesc, acc0);
                     else issue_dispatch<NPASS, false>(nk, acc, 0, 0, ahi, alo, dhi, dlo, idesc, acc0);
-                    umma_commit(&bars->mma_done[t][net]);
-                    if (t == ntile - 1) umma_commit(&bars->empty[it & smask]);   // all tiles' MMAs done -> slot free
                 }
-                __syncwarp();
-                T3_TR(0x40 + t)          // MMAs of tile t issued + committed
             }
+            if (leader) {
+                umma_commit(&bars->mma_done[t][net]);
+                umma_commit(&bars->empty[it & smask]);      // this tile's MMAs on the chunk done (the barrier counts the tiles)
+            }
+            __syncwarp();
+            T3_TR(0x40 + t)          // MMAs issued + committed
         }
-        // consume the final `fin` phase of both tiles (the q-density epilogues) to stay in step with the groups
-        mbar_wait(&bars->fin[0], fin_c0 & 1u); fin_c0++;
-        if (ntile == 2) { mbar_wait(&bars->fin[1], fin_c1 & 1u); fin_c1++; }
-        ring_it += (uint32_t)ts.nchunks;
+        carried = k_req > nq ? k_req - nq : 0;
+        // consume the final `fin` phase of the tile (the q-density epilogue) to stay in step with its group
+        mbar_wait(&bars->fin[t], fin_c & 1u); fin_c++;
     T3_STEP_END
     T3_ITEM_END
 }
@@ -550,7 +586,6 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
         // HTS: shared addresses of this row inside the first-layer operand tiles [IN hi, IN lo, U hi, U lo] of its tile
         const uint32_t in_row = x.h_base + (uint32_t)((x.row >> 3) * (Kin >> 3) * 128 + (x.row & 7) * 16);
         const uint32_t u_row = x.h_base + 2u * h_stride + (uint32_t)((x.row >> 3) * (Ku >> 3) * 128 + (x.row & 7) * 16);
-        constexpr uint32_t kAcc1 = HTS ? kT3HAcc1 : kT3Acc1;
         // ---- input operand [z (2), cond (C0), prefix (2*step), 0...] ----
         {
             const float* cp = src_at(a.cond, ag, pt, INV ? step : jstep) - 2;     // chain mode: cond[:, j] for every chain step
@@ -588,44 +623,28 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
             // ============ density nets (shift | log-scale): two relu layers ============
 #pragma unroll 1
             for (int l = 0; l < 2; ++l) {
-#if FC_T3_SPLIT_NETS
-                {
-                    const int net = x.part;
-                    const uint32_t bias = x.bias_ring + (uint32_t)(net * 4 + ((x.chunk_it >> 1) & 3)) * kT3BiasEntry;
-                    T3_TR(0x10 + net)
-                    wait_mma3(x, 0);         // every thread tracks both nets' phases; the other net's MMAs were issued earlier
-                    wait_mma3(x, 1);
-                    T3_TR(0x12 + net)
-                    const uint32_t acc = x.tb + (net ? kAcc1 : kT3Acc0);
-                    const uint32_t ohi = HTS ? x.tb + (net ? kT3H1Hi : kT3H0Hi) : x.h_base + (uint32_t)(net * 2) * h_stride;
-                    const uint32_t olo = HTS ? x.tb + (net ? kT3H1Lo : kT3H0Lo) : ohi + h_stride;
-                    epi_layer3<NPASS, ACT_R, false, true, !FOLD_D, HTS>(acc, ohi, olo, bias, 0u, x.part, Wd, koff_d);
-                    warp_arrive3(x, &bars->opnd[g][net]);
-                    x.chunk_it += 2;
-                }
-#else
 #pragma unroll 1
                 for (int net = 0; net < 2; ++net) {
                     const uint32_t bias = x.bias_ring + (uint32_t)(net * 4 + ((x.chunk_it >> 1) & 3)) * kT3BiasEntry;
                     T3_TR(0x10 + net)        // waiting for the MMAs of this net
-                    wait_mma3(x, net);
+                    const uint32_t acc = wait_mma3<HTS>(x, net);
                     T3_TR(0x12 + net)        // accumulator ready: epilogue starts
-                    const uint32_t acc = x.tb + (net ? kAcc1 : kT3Acc0);
-                    const uint32_t ohi = HTS ? x.tb + (net ? kT3H1Hi : kT3H0Hi) : x.h_base + (uint32_t)(net * 2) * h_stride;
-                    const uint32_t olo = HTS ? x.tb + (net ? kT3H1Lo : kT3H0Lo) : ohi + h_stride;
-                    epi_layer3<NPASS, ACT_R, false, true, !FOLD_D, HTS>(acc, ohi, olo, bias, 0u, x.part, Wd, koff_d);
-                    warp_arrive3(x, &bars->opnd[g][net]);
+                    if (HTS) {
+                        epi_inplace3<NPASS, ACT_R, false, true, !FOLD_D>(x, acc, bias, 0u, Wd, &bars->opnd[g][net]);
+                    } else {
+                        const uint32_t ohi = x.h_base + (uint32_t)(net * 2) * h_stride, olo = ohi + h_stride;
+                        epi_layer3<NPASS, ACT_R, false, true, !FOLD_D, false>(acc, ohi, olo, bias, 0u, x.part, Wd, koff_d);
+                        warp_arrive3(x, &bars->opnd[g][net]);
+                    }
                     x.chunk_it++;
                 }
-#endif
             }
             // ---- L3 outputs: means in acc0[0,CPd), log-stddevs in acc1[0,CPd) ----
             const float* bias_mu = reinterpret_cast<const float*>(bias_ring + (size_t)(0 * 4 + ((x.chunk_it >> 1) & 3)) * kT3BiasEntry);
             const float* bias_ls = reinterpret_cast<const float*>(bias_ring + (size_t)(1 * 4 + ((x.chunk_it >> 1) & 3)) * kT3BiasEntry);
             x.chunk_it += 2;
             T3_TR(0x14)              // waiting for both L3 outputs
-            wait_mma3(x, 0);
-            wait_mma3(x, 1);
+            const uint32_t acc_mu = wait_mma3<HTS>(x, 0), acc_ls = wait_mma3<HTS>(x, 1);
             T3_TR(0x15)              // E2 / E3 phase starts
             if (which == 0) {
                 // sample u = exp(ls) eps + mu (fastpredNF.py:727-733) -> [u, mx] operand; log r = -C/2 log 2pi - sum ls - 1/2 sum eps^2
@@ -645,8 +664,8 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
                         float mu[8], ls[8], e[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) e[i] = 0.0f;
-                        tmem_ld8(x.tb + kT3Acc0 + (uint32_t)d0, mu);
-                        tmem_ld8(x.tb + kAcc1 + (uint32_t)d0, ls);
+                        tmem_ld8(acc_mu + (uint32_t)d0, mu);
+                        tmem_ld8(acc_ls + (uint32_t)d0, ls);
                         if (a.eps != nullptr) {
                             const float* ep = a.eps + n * a.eps_rs + (MODE == 1 ? ts.seq_eps_off + (jstep - step) * C : ts.eps_off) + d0;
 #pragma unroll
@@ -692,8 +711,8 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
                 for (int d0 = x.part * 8; d0 < CPd; d0 += 8 * NPARTS) {
                     float mu[8], ls[8];
                     uint32_t uh[4], ul[4];
-                    tmem_ld8(x.tb + kT3Acc0 + (uint32_t)d0, mu);
-                    tmem_ld8(x.tb + kAcc1 + (uint32_t)d0, ls);
+                    tmem_ld8(acc_mu + (uint32_t)d0, mu);
+                    tmem_ld8(acc_ls + (uint32_t)d0, ls);
                     if (HTS) {
                         lds128u(u_row + (uint32_t)(d0 >> 3) * 128u, uh);
                         lds128u(u_row + h_stride + (uint32_t)(d0 >> 3) * 128u, ul);
@@ -730,53 +749,37 @@ __device__ __forceinline__ void t3_compute(const T2Step* __restrict__ steps, con
 #pragma unroll 1
                 for (int l = 0; l <= ts.n_hidden; ++l) {
                     const bool last = l == ts.n_hidden;
-#if FC_T3_SPLIT_NETS
-                    {
-                        const int net = x.part;
-                        const uint32_t tail = x.bias_ring + (uint32_t)(net * 4 + ((x.chunk_it >> 1) & 3)) * kT3BiasEntry;
-                        x.chunk_it += 2;
-                        T3_TR(0x10 + net)
-                        wait_mma3(x, 0);
-                        wait_mma3(x, 1);
-                        T3_TR(0x12 + net)
-                        const uint32_t acc = x.tb + (net ? kAcc1 : kT3Acc0);
-                        const uint32_t ohi = HTS ? x.tb + (net ? kT3H1Hi : kT3H0Hi) : x.h_base + (uint32_t)(net * 2) * h_stride;
-                        const uint32_t olo = HTS ? x.tb + (net ? kT3H1Lo : kT3H0Lo) : ohi + h_stride;
-                        if (!last) {
-                            if (net == 0) epi_layer3<NPASS, ACT_T, false, true, !FOLD_C, HTS>(acc, ohi, olo, tail, 0u, x.part, Hc, koff_c);
-                            else epi_layer3<NPASS, ACT_R, false, true, !FOLD_C, HTS>(acc, ohi, olo, tail, 0u, x.part, Hc, koff_c);
-                            warp_arrive3(x, &bars->opnd[g][net]);
-                        } else {
-                            float pd;
-                            if (net == 0) pd = epi_layer3<NPASS, ACT_T, true, false, !FOLD_C>(acc, ohi, olo, tail, tail + Hc * 4, x.part, Hc, koff_c);
-                            else pd = epi_layer3<NPASS, ACT_R, true, false, !FOLD_C>(acc, ohi, olo, tail, tail + Hc * 4, x.part, Hc, koff_c);
-                            // this part owns the whole dot product of its net: its bias rides in the partial (the other part adds 0)
-                            if (net == 0) ps = pd + lds32(tail + Hc * 8); else pt_ = pd + lds32(tail + Hc * 8);
-                        }
-                    }
-#else
 #pragma unroll 1
                     for (int net = 0; net < 2; ++net) {
                         const uint32_t tail = x.bias_ring + (uint32_t)(net * 4 + ((x.chunk_it >> 1) & 3)) * kT3BiasEntry;
                         x.chunk_it++;
                         T3_TR(0x10 + net)
-                        wait_mma3(x, net);
+                        const uint32_t acc = wait_mma3<HTS>(x, net);
                         T3_TR(0x12 + net)
-                        const uint32_t acc = x.tb + (net ? kAcc1 : kT3Acc0);
-                        const uint32_t ohi = HTS ? x.tb + (net ? kT3H1Hi : kT3H0Hi) : x.h_base + (uint32_t)(net * 2) * h_stride;
-                        const uint32_t olo = HTS ? x.tb + (net ? kT3H1Lo : kT3H0Lo) : ohi + h_stride;
-                        if (!last) {
-                            if (net == 0) epi_layer3<NPASS, ACT_T, false, true, !FOLD_C, HTS>(acc, ohi, olo, tail, 0u, x.part, Hc, koff_c);
-                            else epi_layer3<NPASS, ACT_R, false, true, !FOLD_C, HTS>(acc, ohi, olo, tail, 0u, x.part, Hc, koff_c);
-                            warp_arrive3(x, &bars->opnd[g][net]);
+                        if (HTS) {
+                            if (!last) {
+                                if (net == 0) epi_inplace3<NPASS, ACT_T, false, true, !FOLD_C>(x, acc, tail, 0u, Hc, &bars->opnd[g][net]);
+                                else epi_inplace3<NPASS, ACT_R, false, true, !FOLD_C>(x, acc, tail, 0u, Hc, &bars->opnd[g][net]);
+                            } else {
+                                float pd;
+                                if (net == 0) pd = epi_inplace3<NPASS, ACT_T, true, false, !FOLD_C>(x, acc, tail, tail + Hc * 4, Hc, nullptr);
+                                else pd = epi_inplace3<NPASS, ACT_R, true, false, !FOLD_C>(x, acc, tail, tail + Hc * 4, Hc, nullptr);
+                                if (net == 0) { ps = pd; bs = lds32(tail + Hc * 8); } else { pt_ = pd; bt = lds32(tail + Hc * 8); }
+                            }
                         } else {
-                            float pd;
-                            if (net == 0) pd = epi_layer3<NPASS, ACT_T, true, false, !FOLD_C>(acc, ohi, olo, tail, tail + Hc * 4, x.part, Hc, koff_c);
-                            else pd = epi_layer3<NPASS, ACT_R, true, false, !FOLD_C>(acc, ohi, olo, tail, tail + Hc * 4, x.part, Hc, koff_c);
-                            if (net == 0) { ps = pd; bs = lds32(tail + Hc * 8); } else { pt_ = pd; bt = lds32(tail + Hc * 8); }
+                            const uint32_t ohi = x.h_base + (uint32_t)(net * 2) * h_stride, olo = ohi + h_stride;
+                            if (!last) {
+                                if (net == 0) epi_layer3<NPASS, ACT_T, false, true, !FOLD_C, false>(acc, ohi, olo, tail, 0u, x.part, Hc, koff_c);
+                                else epi_layer3<NPASS, ACT_R, false, true, !FOLD_C, false>(acc, ohi, olo, tail, 0u, x.part, Hc, koff_c);
+                                warp_arrive3(x, &bars->opnd[g][net]);
+                            } else {
+                                float pd;
+                                if (net == 0) pd = epi_layer3<NPASS, ACT_T, true, false, !FOLD_C>(acc, ohi, olo, tail, tail + Hc * 4, x.part, Hc, koff_c);
+                                else pd = epi_layer3<NPASS, ACT_R, true, false, !FOLD_C>(acc, ohi, olo, tail, tail + Hc * 4, x.part, Hc, koff_c);
+                                if (net == 0) { ps = pd; bs = lds32(tail + Hc * 8); } else { pt_ = pd; bt = lds32(tail + Hc * 8); }
+                            }
                         }
                     }
-#endif
                 }
                 // both nets done: affine update of the unmasked coordinate + BatchNorm (TFCondARFlow.py:360-381, 303-315)
                 const float s = row_sum3(x, 0, ps) + bs, t = row_sum3(x, 1, pt_) + bt;
@@ -868,12 +871,13 @@ k_separate_tc3(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
 
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) {
-        for (uint32_t s = 0; s < nslots; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+        // a weight slot is handed back once the issuers of BOTH tiles have committed the MMAs that read it
+        for (uint32_t s = 0; s < nslots; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], dm.single ? 1 : 2); }
         for (int t = 0; t < 2; ++t) {
             mbar_init(&bars->mma_done[t][0], 1);
             mbar_init(&bars->mma_done[t][1], 1);
-            mbar_init(&bars->opnd[t][0], FC_T3_SPLIT_NETS ? 4 : 8);      // warps that run this net's hidden epilogues
-            mbar_init(&bars->opnd[t][1], FC_T3_SPLIT_NETS ? 4 : 8);
+            mbar_init(&bars->opnd[t][0], 8);      // warps that run this net's hidden epilogues
+            mbar_init(&bars->opnd[t][1], 8);
             mbar_init(&bars->fin[t], 8);
         }
         mbar_fence_init();
@@ -892,7 +896,7 @@ k_separate_tc3(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tslot);
 
-    // three roles (inlined: separate noinline role functions measured 3 ms slower)
+    // two roles (inlined: separate noinline role functions measured 3 ms slower)
     // Warp-specialised register split (setmaxnreg, per warpgroup): the kernel launches with 96 registers per thread
     // (640 threads); the service warpgroup (warps 16-19) gives back all but 56, the four epilogue warpgroups grow to 104.
     // setmaxnreg.inc only draws on what .dec released: 4 x 128 x (104 - 96) = 4096 <= 128 x (96 - 56) = 5120.
@@ -901,9 +905,7 @@ k_separate_tc3(const T2Step* __restrict__ steps, const uint8_t* __restrict__ img
         t3_compute<NPASS, FOLD_D, FOLD_C, MODE, HTS>(steps, a, o, dm, pairs_per_step, total_items, smem, tmem_base);
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kT3ServiceRegs));
-        if (warp == 16) t3_producer(steps, img, dm, pairs_per_step, total_items, smem);
-        else if (warp < 19) t3_issuer<NPASS, HTS>(steps, dm, pairs_per_step, total_items, smem, tmem_base, warp - 17);
-        else t3_idle(steps, dm, pairs_per_step, total_items, smem);
+        t3_issuer<NPASS, HTS>(steps, img, dm, pairs_per_step, total_items, smem, tmem_base, (warp - 16) & 1, (warp - 16) >> 1);
     }
 
     tc_fence_before();

@@ -224,20 +224,22 @@ __device__ __forceinline__ void split8(const float* a, uint32_t* hi, uint32_t* l
         }
     }
 }
-// tanh(x) = 1 - 2 / (1 + e^{2x}), |err| ~ 5e-7 (MUFU.TANH itself is only 2^-11 accurate).  Two values share ONE
-// reciprocal (r = 1/(y0 y1), 1/y0 = r y1, 1/y1 = r y0): 1.5 MUFU ops per value instead of 2.
+// tanh|x| = 2 / (1 + q) - 1 with q = e^{-2|x|} in (0, 1] (no overflow, no clamp), sign copied back; |err| ~ 5e-7
+// (MUFU.TANH itself is only 2^-11 accurate).  Two values share ONE reciprocal: with y' = (1 + q) / 2 and
+// r = 1 / (y0' y1') = 4 / (y0 y1), 2 / y0 = y1' r -- 1.5 MUFU + 3.5 ALU instructions per value (-|x| rides on MUFU.EX2).
 // The inputs arrive PRE-SCALED by 2 log2(e) (tc2_pack folds the factor into the s-net weights and biases).
 __device__ __forceinline__ void tanh_acc2(float& x0, float& x1) {
-    float e0, e1;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(x0, 43.0f)));   // clamp: keeps y0*y1 finite, tanh(43 / 2.885) == 1
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(x1, 43.0f)));
-    const float y0 = e0 + 1.0f, y1 = e1 + 1.0f;
+    float q0, q1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(q0) : "f"(-fabsf(x0)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(q1) : "f"(-fabsf(x1)));
+    const float y0 = fmaf(q0, 0.5f, 0.5f), y1 = fmaf(q1, 0.5f, 0.5f);
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y0 * y1));
-    r *= -2.0f;
-    x0 = fmaf(y1, r, 1.0f);
-    x1 = fmaf(y0, r, 1.0f);
+    const float t0 = fmaf(y1, r, -1.0f), t1 = fmaf(y0, r, -1.0f);
+    x0 = __uint_as_float(__float_as_uint(t0) | (__float_as_uint(x0) & 0x80000000u));
+    x1 = __uint_as_float(__float_as_uint(t1) | (__float_as_uint(x1) & 0x80000000u));
 }
+// (Four values sharing one reciprocal -- 1.25 MUFU + 4.25 ALU per value -- measured no faster: 45.9 vs 45.1 ms.)
 __device__ __forceinline__ float tanh_acc(float x) {
     float e;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));

@@ -82,3 +82,14 @@ for w in (0, 8):
     print(f"warp {w}: phase means (cycles) and share of time")
     for g in sorted(acc):
         print(f"   {names.get(g, hex(g)):28s} n={cnt[g]:4d}  mean {acc[g] / cnt[g]:8.0f}  share {100 * acc[g] / tot:5.1f} %")
+
+# ---- optional merged raw timeline (T3_TRACE_DUMP=path): warps 0 / 8 (tile 0 / 1, part 0), 4 / 12 (part 1), issuers 17 / 18 ----
+dump = os.environ.get("T3_TRACE_DUMP")
+if dump:
+    allev = []
+    for w in range(20):
+        allev += [(t, w, g) for t, g in events(w)]
+    allev.sort()
+    t0 = allev[0][0]
+    with open(dump, "w") as fh:
+        for t, w, g in allev: fh.write(f"{t - t0:9d} w{w:02d} {g:#04x}\n")
