@@ -54,11 +54,26 @@ __device__ __forceinline__ unsigned long long global_ns() {
     return t;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;          // fast path (already complete)
-    const unsigned long long t0 = global_ns();
-#pragma unroll 1                                      // keep every wait site a handful of instructions (I-cache!)
-    while (!mbar_try_wait(bar, parity))
-        if (global_ns() - t0 > 4000000000ull) __trap();      // 4 s: no legitimate wait in these kernels is longer than milliseconds
+    // The poll loop is hot (ncu: with a timer read per poll the wait loops of the two-tile kernel were ~10 % of all executed
+    // instructions), so it is five instructions in PTX and bounded by a poll count: 2^24 polls are >= 0.2 s even if every
+    // try_wait returned at once (it suspends for a hardware-chosen time first), far beyond any legitimate wait here.
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .u32 n;\n\t"
+        "mov.u32 n, 0;\n"
+        "WAIT_%=:\n\t"
+#if FC_MBAR_HINT
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
+#else
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+#endif
+        "@p bra DONE_%=;\n\t"
+        "add.u32 n, n, 1;\n\t"
+        "setp.lt.u32 q, n, 0x1000000;\n\t"
+        "@q bra WAIT_%=;\n\t"
+        "trap;\n"
+        "DONE_%=:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
 }
 
 // ---- 1-D bulk copy global -> shared (TMA engine, completes on an mbarrier) -----------------------
