@@ -1,6 +1,6 @@
 // Microbenchmark (development aid): issue rate of the instructions the f16x3 operand split is made of, per SM per clock,
 // with 16 warps resident (4 per scheduler) and 8 independent chains per thread.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mb_alu mb_alu.cu && ./mb_alu
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/mb_alu_bin tools/mb_alu.cu
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>

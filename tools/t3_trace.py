@@ -49,26 +49,20 @@ print("epilogue warps (lane 0 of the first warp of each column part), share of t
 for w in (0, 4, 8, 12):
     b, p, wt, tot, n = summarize_compute(w)
     if tot: print(f"  warp {w:2d} (tile {w // 8}, part {(w // 4) % 2}): epilogue+tails {100 * b / tot:5.1f} %  E2/E3 {100 * p / tot:5.1f} %  waiting for MMAs {100 * wt / tot:5.1f} %  ({n} events, {tot} cycles)")
-for w in (17, 18):
+for w in (16, 17, 18, 19):      # issuers: (net, tile) = ((w - 16) & 1, (w - 16) >> 1)
     ev = events(w)
-    wait_w = wait_o = issue = 0
+    prep = wait_w = wait_o = issue = req = 0
     for (t0, g0), (t1, g1) in zip(ev, ev[1:]):
         if t1 < t0: continue
         d = t1 - t0
-        if g1 == 0x20: wait_w += d                       # until the weight chunk landed
+        if g1 == 0x22: prep += d                         # loop back + descriptors of the next chunk
+        elif g1 == 0x20: wait_w += d                     # until the weight chunk landed
         elif g1 in (0x30, 0x31): wait_o += d             # until the operand was ready
-        elif g1 in (0x40, 0x41): issue += d              # issuing MMAs
-    tot = wait_w + wait_o + issue
-    if tot: print(f"  issuer warp {w}: waiting for weights {100 * wait_w / tot:5.1f} %  waiting for operands {100 * wait_o / tot:5.1f} %  issuing {100 * issue / tot:5.1f} %")
-# a short raw timeline of one steady-state stretch
-allev = []
-for w in (16, 17):
-    allev += [(t, w, g) for t, g in events(w)[200:280]]
-allev.sort()
-if allev:
-    t0 = allev[0][0]
-    for t, w, g in allev[:150]: print(f"{t - t0:8d}  warp {w:2d}  tag {g:#x}")
-
+        elif g1 in (0x40, 0x41): issue += d              # issuing MMAs + commits
+        elif g1 in (0x50, 0x51, 0x52, 0x53): req += d    # weight-ring requests (last-tile issuers)
+    tot = prep + wait_w + wait_o + issue + req
+    if tot: print(f"  issuer warp {w} (net {(w - 16) & 1}, tile {(w - 16) >> 1}): bookkeeping {100 * prep / tot:5.1f} %  ring requests {100 * req / tot:5.1f} %  "
+                  f"waiting for weights {100 * wait_w / tot:5.1f} %  waiting for operands {100 * wait_o / tot:5.1f} %  issuing {100 * issue / tot:5.1f} %")
 # ---- per-phase durations of one epilogue warp (mean cycles between consecutive tags) ----
 names = {0x10: "wait MMA net0", 0x11: "wait MMA net1", 0x12: "epilogue net0", 0x13: "epilogue net1", 0x14: "wait both L3",
          0x15: "E2/E3 gaussian phase", 0x16: "coupling tail / gather"}
