@@ -40,6 +40,30 @@ METRIC = "log_density_evals_per_sec"
 UNIT = "evals/s"
 
 
+class _OneLineStdout:
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on stdout from C
+    code when NCCL_DEBUG or an nccl.conf asks for it), so for the whole run file descriptor 1 points at stderr and the
+    JSON line is written to the saved, real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, obj):
+        os.write(self._real, (json.dumps(obj) + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._real, 1)
+        os.close(self._real)
+        return False
+
+
+OUT = None      # set by main()
+
+
 def ncu_traffic(precision: str):
     """DRAM bytes (read + write) of ONE pass of the dominant kernel, from the committed `ncu --set full` capture of this
     same command (profiles/).  The f16x3 kernel (k_separate_tc3) covers the 12 steps with two launches (one per weight
@@ -325,7 +349,7 @@ def run_reference(args):
                        "sample": sample, "note": "rate metric (evals/s): the CPU arm runs a bounded sample of the same per-row work"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    OUT.emit(line)
     del limiter
 
 
@@ -603,7 +627,7 @@ def run_ours(args):
                 line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": blas_threads(), "kind": "port",
                                         "sample": f"1 agent x 100x100 lattice x {T} steps (config 1 shape), numpy fp32 port, "
                                                   f"median of {nrep} passes ({med * 1e3:.0f} ms each)"}
-        print(json.dumps(line))
+        OUT.emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -626,10 +650,12 @@ def main():
     ap.add_argument("--gather", default="auto", choices=["auto", "nccl", "multicast"],
                     help="multi-GPU assembly of the maps: multicast stores fused into the kernel, or NCCL all-gather")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    global OUT
+    with _OneLineStdout() as OUT:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
 
 
 if __name__ == "__main__":

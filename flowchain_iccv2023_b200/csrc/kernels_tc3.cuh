@@ -1,14 +1,13 @@
 // kernels_tc3.cuh -- f16x3 / f16 tensor-core per-step density with TWO resident 128-row tiles per CTA.
 //
 // Split-fp16 operands, tcgen05.mma, fp32 accumulate (arithmetic helpers and the weight image: tc_f16x3.cuh), organised so
-// that two independent tiles share one SM: tensor memory can hold only one tile when every operand lives in it
-// (480 of 512 columns), so here the HIDDEN-layer operands go to shared memory (SS-mode MMA, canonical K-major tiles
-// written by the epilogue) and tensor memory keeps just the accumulators and the two narrow first-layer operands
-// ([z|w, y] and [u, mx], TS-mode) -- 256 columns per tile.  Two groups of 8 epilogue warps each own a tile and run
-// the unchanged per-tile schedule; they share the TMA weight ring (one chunk feeds both tiles: half the L2 traffic
-// per row) and the two MMA-issuer warps (one per net, serving tile 0 then tile 1 for every net-layer).  The groups'
-// epilogues overlap each other and the other tile's MMAs, which hides the MMA -> epilogue -> MMA latency chain that
-// bounds the single-tile kernel.
+// that two independent tiles share one SM and 256 tensor-memory columns each.  Two groups of 8 epilogue warps own a tile
+// each; the service warpgroup is four MMA issuers, one per (net, tile), and the issuers of the last tile also feed the
+// TMA weight ring (one chunk serves both tiles: half the L2 traffic per row).  The groups' epilogues overlap each other
+// and the other tile's MMAs, which hides most of the MMA -> epilogue -> MMA latency chain that bounds a single tile.
+// Two tensor-memory layouts (see the column map below): hidden operands in tensor memory, converted in place over
+// ping-pong accumulator regions (layers <= 64 wide), or hidden operands in shared memory (layers up to 80 wide, chain
+// mode, sampler).
 #pragma once
 #include "kernels_fp32.cuh"
 #include "tc_f16x3.cuh"
@@ -48,7 +47,7 @@ struct T3Dims {
                                 // 2: sampler (flow.sample_with_log_prob): item = tiles, inverse steps 0 .. T-1
     int32_t klo, jlo;           // chain mode: lowest chain step applied, first result index written
     int32_t no_fold;            // 1: ignore the chunks' bias tiles (launches whose steps mix folded and plain widths)
-    int32_t single;             // 1: one tile per item (group 1 idles): small launches that would leave SMs empty otherwise
+    int32_t single;             // 1: one tile per item (group 1 and its issuers idle): small launches that would leave SMs empty otherwise
 };
 
 // development aid (-DFC_T3_TRACE=1): lane 0 of every warp of CTA 0 logs (tag << 48 | clock) events of one launch
