@@ -116,3 +116,33 @@ def test_wrapper_load_rejects_mismatched_flow_keys(tmp_path):
     torch.save({"epoch": 9, "state": state, "optim_state": {}}, path)
     with pytest.raises(RuntimeError, match="does not match"):
         m.load(path)
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py's contract: ONE JSON line on stdout (the driver parses it); everything else -- library banners included,
+    which is why bench.py points file descriptor 1 at stderr for the run -- goes to stderr.  The reference arm runs on the
+    host cores, so the contract can be checked here."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.splitlines()
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["metric"] and d["unit"]
+
+
+def test_bench_own_arm_refuses_without_gpu():
+    """No CPU fallback: without a CUDA device the product arm exits non-zero and prints nothing on stdout."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode != 0 and r.stdout == "" and "no CPU fallback" in r.stderr
