@@ -17,9 +17,14 @@ __device__ __forceinline__ bool test_wait(uint64_t* bar, uint32_t parity) {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool try_wait_hint(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 template <int MODE>
 __device__ __forceinline__ void wait_mode(uint64_t* bar, uint32_t parity) {
-    if (MODE == 0) mbar_wait(bar, parity);
+    if (MODE == 0) { while (!try_wait_hint(bar, parity)) {} }
     else if (MODE == 1) { while (!try_wait_plain(bar, parity)) {} }
     else { while (!test_wait(bar, parity)) {} }
 }
